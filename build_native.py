@@ -1,0 +1,42 @@
+"""Build libstv_b200.so in-tree with nvcc for sm_100a (no GPU needed: nvcc cross-compiles)."""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "style_transfer_visualizer_b200" / "csrc"
+OUT = ROOT / "style_transfer_visualizer_b200" / "lib" / "libstv_b200.so"
+SOURCES = ["api.cu", "conv_igemm.cu", "gram.cu", "conv_direct.cu", "elementwise.cu"]
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def needs_rebuild() -> bool:
+    if not OUT.exists():
+        return True
+    newest = max(p.stat().st_mtime for p in list(CSRC.iterdir()) + [ROOT / "include" / "stv_b200.h"])
+    return newest > OUT.stat().st_mtime
+
+
+def build(*, force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_rebuild():
+        return OUT
+    OUT.parent.mkdir(parents=True, exist_ok=True)
+    cmd = ["nvcc", *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT),
+           *[str(CSRC / s) for s in SOURCES]]
+    proc = subprocess.run(cmd, capture_output=True, text=True, check=False)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        msg = f"nvcc failed with exit code {proc.returncode}"
+        raise RuntimeError(msg)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

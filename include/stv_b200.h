@@ -1,0 +1,139 @@
+/*
+ * stv_b200.h -- C ABI of the B200-native style-transfer optimisation step.
+ *
+ * The reference (bjg-gh/style_transfer_visualizer) has no FFI: its hot path calls straight into
+ * PyTorch from Python.  Each entry point below therefore names the reference call site whose
+ * device work it replaces (paths relative to src/style_transfer_visualizer/ in the reference).
+ * The Python package binds these with ctypes and exposes them as torch.library custom ops
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; memory is owned by the caller (PyTorch's
+ *     caching allocator in the shipped host code); kernels never allocate;
+ *   - activations are NHWC fp32 ([H][W][C], C innermost); the image itself and its gradient are
+ *     NCHW fp32 exactly as the reference holds them ([1,3,H,W]);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises,
+ *     so every call is CUDA-graph capturable;
+ *   - return value 0 = ok, non-zero = error; stv_last_error() returns a thread-local message;
+ *   - the library refuses to run on anything but compute capability 10.x (no fallback path).
+ */
+#ifndef STV_B200_H_
+#define STV_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STV_ABI_VERSION 1
+
+const char* stv_last_error(void);
+int stv_abi_version(void);
+/* 0 when the current device is sm_100-class, else non-zero (with stv_last_error set). */
+int stv_device_check(void);
+
+/* ---- weights (one-off; weights are frozen: core_model.py:103-117) ------------------------- */
+/* w: torch Conv2d layout [Cout][Cin][3][3].  w_fwd: [9][Cout][Cin]; w_dgrad: [9][Cin][Cout] with
+ * the taps flipped (either output may be NULL). */
+int stv_pack_conv_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin,
+                          void* stream);
+
+/* ---- VGG conv stack: forward (core_model.py:316 `x = block(x)`, torchvision Conv2d+ReLU) --- */
+/* conv1_1: image NCHW [3][H][W] -> NHWC [H][W][64].  out_pre = conv + bias, out_post = relu of it;
+ * either may be NULL. */
+int stv_conv3x3_first_fwd(const float* img_nchw, const float* w /*[64][3][3][3]*/,
+                          const float* bias, int H, int W, int Cout, float* out_pre,
+                          float* out_post, void* stream);
+/* 3x3 pad-1 conv on the tensor cores (tcgen05, TF32 multiply, FP32 accumulate).
+ * x: NHWC [H][W][Cin], w_fwd from stv_pack_conv_weights, Cin % 32 == 0, Cout % 64 == 0. */
+int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
+                    int Cout, float* out_pre, float* out_post, void* stream);
+
+/* ---- VGG conv stack: input gradient (autograd of the above; optimization.py:313) ---------- */
+/* dx = [relu_src > 0] .* conv_transpose(dy) (+ dx when accumulate != 0).
+ * dy: NHWC [H][W][Cout]; dx, relu_src: NHWC [H][W][Cin]; relu_src may be NULL (no gating).
+ * w_dgrad from stv_pack_conv_weights.  Cout % 32 == 0, Cin % 64 == 0. */
+int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                      const float* relu_src, int accumulate, float* dx, void* stream);
+/* conv1_1 input gradient: dy NHWC [H][W][64] -> dimg NCHW [3][H][W] (this is input_img.grad). */
+int stv_conv3x3_first_dgrad(const float* dy, const float* w /*[64][3][3][3]*/, int H, int W,
+                            int Cout, float* dimg_nchw, void* stream);
+
+/* ---- pooling / ReLU (torchvision MaxPool2d(2,2), nn.ReLU; core_model.py:134-135) ----------- */
+int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream);
+/* dx = route(dy) to the first max of each 2x2 window; relu_mask != 0 additionally gates by x > 0. */
+int stv_maxpool2_bwd(const float* dy, const float* x, int H, int W, int C, int relu_mask, float* dx,
+                     void* stream);
+int stv_relu_fwd(const float* x, long n, float* y, void* stream);
+int stv_relu_bwd(const float* dy, const float* x, long n, int accumulate, float* dx, void* stream);
+int stv_add_inplace(float* dst, const float* src, long n, void* stream);
+
+/* ---- style loss: gram_matrix + mse_loss (core_model.py:29-63, :234-264) ------------------- */
+size_t stv_gram_workspace_bytes(long hw, int C);
+/* x: NHWC features [hw][C].  Computes R = F F^T on the tensor cores (upper triangle, split-K),
+ * G = min(R, clamp_max) / (C*hw).  Optional outputs (NULL to skip):
+ *   gram_out [C][C] = G;   loss_out[0] = mean((G - target)^2);
+ *   s_out   [C][C] = 4/(C^2 * C*hw) * 1[R <= clamp_max] * (G - target)   (backward seed). */
+int stv_gram_loss_fwd(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
+                      const float* target, float clamp_max, float* gram_out, float* s_out,
+                      float* loss_out, void* stream);
+/* Backward of the above w.r.t. the features: dy (+)= grad_w[0] * x * S   (one GEMM instead of the
+ * two that torch.mm's autograd issues).  grad_w is a DEVICE scalar (upstream dL/dloss). */
+int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* grad_w,
+                  int accumulate, float* dy, void* stream);
+
+/* ---- content loss: mse_loss(F, T) (core_model.py:266-295) --------------------------------- */
+/* partials: scratch of stv_reduce_scratch_floats() floats. */
+int stv_reduce_scratch_floats(void);
+int stv_content_loss_fwd(const float* f, const float* t, long n, float* partials, float* loss_out,
+                         void* stream);
+/* df (+)= grad_w[0] * 2 (f - t) / n */
+int stv_content_loss_bwd(const float* f, const float* t, long n, const float* grad_w,
+                         int accumulate, float* df, void* stream);
+
+/* ---- image update (torch.optim.Adam / LBFGS on the image; optimization.py:175) ------------ */
+int stv_adam_step(float* x, const float* g, float* m, float* v, long n, float beta1, float beta2,
+                  float eps, float step_size, float bias2_sqrt, void* stream);
+/* Same update with the step counter on the device: state[0] = t (incremented here),
+ * state[1..2] = derived scalars.  Needs no host values that change per step => graph replayable. */
+int stv_adam_step_dev(float* x, const float* g, float* m, float* v, long n, float lr, float beta1,
+                      float beta2, float eps, float* state3, void* stream);
+int stv_dot(const float* a, const float* b, long n, float* partials, float* out, void* stream);
+/* out2[0] = max |a_i|, out2[1] = sum |a_i|; partials: 2 * stv_reduce_scratch_floats() floats. */
+int stv_absmax_sum(const float* a, long n, float* partials, float* out2, void* stream);
+/* y += alpha * x ; alpha read from alpha_dev[0] when non-NULL, else alpha_host. */
+int stv_axpy(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
+             void* stream);
+/* y = alpha * x */
+int stv_scale(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
+              void* stream);
+
+/* ---- timelapse frame readback (image_io.py:129-152, optimization.py:438-452) --------------- */
+/* img NCHW [3][H][W] -> out HWC uint8.  denormalize: apply ImageNet std/mean first.
+ * rounding 0 = truncate (timelapse frames), 1 = round-half-even (final frame, main.py:203-214). */
+int stv_frame_to_u8(const float* img_nchw, int H, int W, int denormalize, int rounding,
+                    unsigned char* out_hwc, void* stream);
+
+/* ---- misc --------------------------------------------------------------------------------- */
+int stv_nchw_to_nhwc(const float* src, int C, int H, int W, float* dst, void* stream);
+int stv_nhwc_to_nchw(const float* src, int C, int H, int W, float* dst, void* stream);
+/* flags[i] |= !isfinite(vals[i]), i < n <= 32 (optimization.py:375-391, checked lazily). */
+int stv_finite_flags(const float* vals, int n, int* flags, void* stream);
+
+/* ---- test hooks ---------------------------------------------------------------------------- */
+/* Explicit tile selection for the tensor-core conv: out = alpha*conv(x,w)+bias, optional relu gate /
+ * accumulate, as in stv_conv3x3_fwd / _dgrad.  taps = 9 or 1; block_n in {64,128,256} or 0 = auto;
+ * th*tw == 128 or 0 = auto. */
+int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                      const float* bias, const float* alpha, const float* mask_src,
+                      const float* add_src, float* out_pre, float* out_post, int block_n, int th,
+                      int tw, void* stream);
+/* Naive CUDA-core NHWC conv, same packed weights; on-device cross-check only. */
+int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
+                 int N, int taps, int relu, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STV_B200_H_ */

@@ -1,0 +1,222 @@
+// C-ABI surface (include/stv_b200.h) over the kernel launchers, plus the shared host utilities:
+// thread-local error string, cached device properties and the TMA descriptor encoder.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/stv_b200.h"
+#include "stv_common.cuh"
+#include "stv_kernels.h"
+
+namespace stv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  STV_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  STV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned",
+              base);
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    STV_REQUIRE(gstr[i] % 16 == 0, "TMA stride %llu not a multiple of 16 bytes",
+                (unsigned long long)gstr[i]);
+  }
+  const CUresult r =
+      fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank),
+         const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  STV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static int check_device_impl() {
+  int dev = 0;
+  STV_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  STV_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  STV_REQUIRE(major == 10,
+              "stv_b200 kernels are built for sm_100a only; device %d has compute capability %d.x "
+              "(no fallback path)",
+              dev, major);
+  return 0;
+}
+
+}  // namespace stv
+
+using namespace stv;
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+const char* stv_last_error(void) { return last_error(); }
+int stv_abi_version(void) { return STV_ABI_VERSION; }
+int stv_device_check(void) { return check_device_impl(); }
+
+int stv_pack_conv_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin,
+                          void* stream) {
+  return pack_conv_weights_launch(w, w_fwd, w_dgrad, Cout, Cin, S(stream));
+}
+
+int stv_conv3x3_first_fwd(const float* img_nchw, const float* w, const float* bias, int H, int W,
+                          int Cout, float* out_pre, float* out_post, void* stream) {
+  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, S(stream));
+}
+
+int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
+                    int Cout, float* out_pre, float* out_post, void* stream) {
+  return conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
+                           out_post, 0, 0, 0, S(stream));
+}
+
+int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                      const float* relu_src, int accumulate, float* dx, void* stream) {
+  return conv_igemm_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
+                           accumulate ? dx : nullptr, dx, nullptr, 0, 0, 0, S(stream));
+}
+
+int stv_conv3x3_first_dgrad(const float* dy, const float* w, int H, int W, int Cout,
+                            float* dimg_nchw, void* stream) {
+  return conv_first_dgrad_launch(dy, w, H, W, Cout, dimg_nchw, S(stream));
+}
+
+int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream) {
+  return maxpool2_fwd_launch(x, H, W, C, y, S(stream));
+}
+int stv_maxpool2_bwd(const float* dy, const float* x, int H, int W, int C, int relu_mask, float* dx,
+                     void* stream) {
+  return maxpool2_bwd_launch(dy, x, H, W, C, relu_mask, dx, S(stream));
+}
+int stv_relu_fwd(const float* x, long n, float* y, void* stream) {
+  return relu_fwd_launch(x, n, y, S(stream));
+}
+int stv_relu_bwd(const float* dy, const float* x, long n, int accumulate, float* dx, void* stream) {
+  return relu_bwd_launch(dy, x, n, accumulate, dx, S(stream));
+}
+int stv_add_inplace(float* dst, const float* src, long n, void* stream) {
+  return add_inplace_launch(dst, src, n, S(stream));
+}
+
+size_t stv_gram_workspace_bytes(long hw, int C) { return gram_workspace_bytes(hw, C); }
+int stv_gram_loss_fwd(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
+                      const float* target, float clamp_max, float* gram_out, float* s_out,
+                      float* loss_out, void* stream) {
+  return gram_launch(x, hw, C, workspace, workspace_bytes, target, clamp_max, gram_out, s_out,
+                     loss_out, S(stream));
+}
+int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* grad_w,
+                  int accumulate, float* dy, void* stream) {
+  // dY[p, :] = grad_w * X[p, :] * S  -- a 1x1 "conv" over a (1 x hw) image with weight matrix S
+  // (symmetric, so its rows serve directly as the K-major B operand).
+  STV_REQUIRE(hw <= 0x7fffffffL, "style_bwd: feature map too large");
+  return conv_igemm_launch(x, s, 1, static_cast<int>(hw), C, C, 1, nullptr, grad_w, nullptr,
+                           accumulate ? dy : nullptr, dy, nullptr, 0, 1, 128, S(stream));
+}
+
+int stv_reduce_scratch_floats(void) { return reduce_scratch_floats(); }
+int stv_content_loss_fwd(const float* f, const float* t, long n, float* partials, float* loss_out,
+                         void* stream) {
+  return content_fwd_launch(f, t, n, partials, loss_out, S(stream));
+}
+int stv_content_loss_bwd(const float* f, const float* t, long n, const float* grad_w,
+                         int accumulate, float* df, void* stream) {
+  return content_bwd_launch(f, t, n, grad_w, accumulate, df, S(stream));
+}
+
+int stv_adam_step(float* x, const float* g, float* m, float* v, long n, float beta1, float beta2,
+                  float eps, float step_size, float bias2_sqrt, void* stream) {
+  return adam_step_launch(x, g, m, v, n, beta1, beta2, eps, step_size, bias2_sqrt, S(stream));
+}
+int stv_adam_step_dev(float* x, const float* g, float* m, float* v, long n, float lr, float beta1,
+                      float beta2, float eps, float* state3, void* stream) {
+  return adam_step_dev_launch(x, g, m, v, n, lr, beta1, beta2, eps, state3, S(stream));
+}
+int stv_dot(const float* a, const float* b, long n, float* partials, float* out, void* stream) {
+  return dot_launch(a, b, n, partials, out, S(stream));
+}
+int stv_absmax_sum(const float* a, long n, float* partials, float* out2, void* stream) {
+  return absmax_sum_launch(a, n, partials, out2, S(stream));
+}
+int stv_axpy(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
+             void* stream) {
+  return axpy_launch(alpha_dev, alpha_host, x, y, n, S(stream));
+}
+int stv_scale(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
+              void* stream) {
+  return scale_launch(alpha_dev, alpha_host, x, y, n, S(stream));
+}
+
+int stv_frame_to_u8(const float* img_nchw, int H, int W, int denormalize, int rounding,
+                    unsigned char* out_hwc, void* stream) {
+  return frame_to_u8_launch(img_nchw, H, W, denormalize, rounding, out_hwc, S(stream));
+}
+int stv_nchw_to_nhwc(const float* src, int C, int H, int W, float* dst, void* stream) {
+  return nchw_to_nhwc_launch(src, C, H, W, dst, S(stream));
+}
+int stv_nhwc_to_nchw(const float* src, int C, int H, int W, float* dst, void* stream) {
+  return nhwc_to_nchw_launch(src, C, H, W, dst, S(stream));
+}
+int stv_finite_flags(const float* vals, int n, int* flags, void* stream) {
+  return finite_flags_launch(vals, n, flags, S(stream));
+}
+
+int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                      const float* bias, const float* alpha, const float* mask_src,
+                      const float* add_src, float* out_pre, float* out_post, int block_n, int th,
+                      int tw, void* stream) {
+  return conv_igemm_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
+                           out_post, block_n, th, tw, S(stream));
+}
+int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
+                 int N, int taps, int relu, float* out, void* stream) {
+  return conv_ref_launch(x, w_packed, bias, H, W, C, N, taps, relu, out, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// CUDA-core convolutions for the 3-channel image boundary of the VGG stack, plus a naive generic
+// NHWC convolution used only as an on-device cross-check in the tests.
+//
+//   conv_first_fwd   : conv1_1 forward, 3 -> 64 channels.  Reads the optimised image in the
+//                      reference's own NCHW layout (core_model.py:316, first block) and writes
+//                      NHWC activations for the tensor-core layers.  K = 27, so the layer is
+//                      HBM-write bound (64 fp32 per pixel out, 3 in); fp32 FMA on CUDA cores.
+//   conv_first_dgrad : input gradient of conv1_1, 64 -> 3 channels, written as NCHW so that it
+//                      is directly `input_img.grad` (optimization.py:313).  N = 3: no tensor-core
+//                      shape fits; HBM-read bound.
+#include "stv_common.cuh"
+#include "stv_kernels.h"
+
+namespace stv {
+
+constexpr int kFirstCout = 64;
+
+// 256 threads = 64 pixels x 4 channel groups; thread cg owns channels {16*i + 4*cg + 0..3}.
+__global__ void __launch_bounds__(256)
+conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                      const float* __restrict__ bias, int H, int W, float* __restrict__ out_pre,
+                      float* __restrict__ out_post) {
+  __shared__ float4 ws[27][kFirstCout / 4];  // ws[k][c/4] = w[c..c+3][k], k = ci*9 + ky*3 + kx
+  __shared__ float4 bs[kFirstCout / 4];
+  for (int i = threadIdx.x; i < 27 * kFirstCout; i += 256) {
+    const int c = i / 27, k = i % 27;  // torch layout [Cout][3][3][3]
+    reinterpret_cast<float*>(&ws[k][c >> 2])[c & 3] = w[i];
+  }
+  if (threadIdx.x < kFirstCout)
+    reinterpret_cast<float*>(bs)[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+
+  const long hw = static_cast<long>(H) * W;
+  const long pix = static_cast<long>(blockIdx.x) * 64 + (threadIdx.x >> 2);
+  if (pix >= hw) return;
+  const int cg = threadIdx.x & 3;
+  const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+        in[ci * 9 + ky * 3 + kx] = ok ? __ldg(img + ci * hw + static_cast<long>(yy) * W + xx) : 0.f;
+      }
+
+  float* pre = out_pre ? out_pre + pix * kFirstCout : nullptr;
+  float* post = out_post ? out_post + pix * kFirstCout : nullptr;
+#pragma unroll
+  for (int i = 0; i < kFirstCout / 16; ++i) {
+    const int c4 = i * 4 + cg;  // float4 index of this thread's 4 channels
+    float4 acc = bs[c4];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 wk = ws[k][c4];
+      acc.x = fmaf(in[k], wk.x, acc.x);
+      acc.y = fmaf(in[k], wk.y, acc.y);
+      acc.z = fmaf(in[k], wk.z, acc.z);
+      acc.w = fmaf(in[k], wk.w, acc.w);
+    }
+    if (pre) reinterpret_cast<float4*>(pre)[c4] = acc;
+    if (post) {
+      float4 o;
+      o.x = fmaxf(acc.x, 0.f); o.y = fmaxf(acc.y, 0.f);
+      o.z = fmaxf(acc.z, 0.f); o.w = fmaxf(acc.w, 0.f);
+      reinterpret_cast<float4*>(post)[c4] = o;
+    }
+  }
+}
+
+// One thread per image pixel; dY (NHWC, 64 ch) neighbours come through L1 (each element is reused
+// by the 9 surrounding pixels of the same CTA row segment).
+__global__ void __launch_bounds__(128)
+conv_first_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int H, int W,
+                        float* __restrict__ dimg) {
+  // wt[tap][co] = {w[co][0][ky][kx], w[co][1][ky][kx], w[co][2][ky][kx], 0}
+  __shared__ float4 wt[9][kFirstCout];
+  for (int i = threadIdx.x; i < 9 * kFirstCout; i += 128) {
+    const int tap = i / kFirstCout, co = i % kFirstCout;
+    float4 v;
+    v.x = w[(co * 3 + 0) * 9 + tap];
+    v.y = w[(co * 3 + 1) * 9 + tap];
+    v.z = w[(co * 3 + 2) * 9 + tap];
+    v.w = 0.f;
+    wt[tap][co] = v;
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y - (ky - 1);
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x - (kx - 1);
+      if (xx < 0 || xx >= W) continue;
+      const float4* src =
+          reinterpret_cast<const float4*>(dy + (static_cast<long>(yy) * W + xx) * kFirstCout);
+      const float4* wk = wt[ky * 3 + kx];
+#pragma unroll 4
+      for (int c4 = 0; c4 < kFirstCout / 4; ++c4) {
+        const float4 g = __ldg(src + c4);
+        const float4 w0 = wk[c4 * 4 + 0], w1 = wk[c4 * 4 + 1], w2 = wk[c4 * 4 + 2],
+                     w3 = wk[c4 * 4 + 3];
+        a0 = fmaf(g.x, w0.x, a0); a1 = fmaf(g.x, w0.y, a1); a2 = fmaf(g.x, w0.z, a2);
+        a0 = fmaf(g.y, w1.x, a0); a1 = fmaf(g.y, w1.y, a1); a2 = fmaf(g.y, w1.z, a2);
+        a0 = fmaf(g.z, w2.x, a0); a1 = fmaf(g.z, w2.y, a1); a2 = fmaf(g.z, w2.z, a2);
+        a0 = fmaf(g.w, w3.x, a0); a1 = fmaf(g.w, w3.y, a1); a2 = fmaf(g.w, w3.z, a2);
+      }
+    }
+  }
+  const long hw = static_cast<long>(H) * W;
+  const long o = static_cast<long>(y) * W + x;
+  dimg[o] = a0;
+  dimg[hw + o] = a1;
+  dimg[2 * hw + o] = a2;
+}
+
+// Naive NHWC conv with packed weights [tap][N][C]; one thread per (pixel, n).  Test-only.
+__global__ void conv_ref_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                const float* __restrict__ bias, int H, int W, int C, int N,
+                                int taps, int relu, float* __restrict__ out) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(H) * W * N;
+  if (idx >= total) return;
+  const int n = static_cast<int>(idx % N);
+  const long pix = idx / N;
+  const int py = static_cast<int>(pix / W), px = static_cast<int>(pix % W);
+  float acc = bias ? bias[n] : 0.f;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
+    const int yy = py + dy, xx = px + dx;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float* xr = x + (static_cast<long>(yy) * W + xx) * C;
+    const float* wr = wp + (static_cast<long>(tap) * N + n) * C;
+    for (int c = 0; c < C; ++c) acc = fmaf(xr[c], wr[c], acc);
+  }
+  out[idx] = relu ? fmaxf(acc, 0.f) : acc;
+}
+
+int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
+                          int Cout, float* out_pre, float* out_post, cudaStream_t stream) {
+  STV_REQUIRE(Cout == kFirstCout, "conv_first_fwd: Cout must be %d (got %d)", kFirstCout, Cout);
+  STV_REQUIRE(out_pre || out_post, "conv_first_fwd: no output buffer");
+  const long hw = static_cast<long>(H) * W;
+  const unsigned blocks = static_cast<unsigned>((hw + 63) / 64);
+  conv_first_fwd_kernel<<<blocks, 256, 0, stream>>>(img_nchw, w, bias, H, W, out_pre, out_post);
+  STV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
+                            float* dimg_nchw, cudaStream_t stream) {
+  STV_REQUIRE(Cout == kFirstCout, "conv_first_dgrad: Cout must be %d (got %d)", kFirstCout, Cout);
+  dim3 grid((W + 127) / 128, H);
+  conv_first_dgrad_kernel<<<grid, 128, 0, stream>>>(dy, w, H, W, dimg_nchw);
+  STV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
+                    int N, int taps, int relu, float* out, cudaStream_t stream) {
+  const long total = static_cast<long>(H) * W * N;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  conv_ref_kernel<<<blocks, 256, 0, stream>>>(x, w_packed, bias, H, W, C, N, taps, relu, out);
+  STV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace stv

@@ -1,0 +1,61 @@
+// Internal launch functions shared between translation units (the C-ABI in api.cu wraps these).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace stv {
+
+// conv_igemm.cu ---------------------------------------------------------------------------
+// out = [relu-mask](alpha * conv(x, w) + bias) + add ; writes out_pre and/or relu(out) to out_post.
+// block_n / th / tw <= 0 select the heuristics.
+int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                      const float* bias, const float* alpha, const float* mask_src,
+                      const float* add_src, float* out_pre, float* out_post, int block_n, int th,
+                      int tw, cudaStream_t stream);
+
+// gram.cu ---------------------------------------------------------------------------------
+size_t gram_workspace_bytes(long hw, int C);
+int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
+                const float* target, float clamp_max, float* gram_out, float* s_out,
+                float* loss_out, cudaStream_t stream);
+
+// conv_direct.cu --------------------------------------------------------------------------
+int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
+                          int Cout, float* out_pre, float* out_post, cudaStream_t stream);
+int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
+                            float* dimg_nchw, cudaStream_t stream);
+int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
+                    int N, int taps, int relu, float* out, cudaStream_t stream);
+
+// elementwise.cu --------------------------------------------------------------------------
+int pack_conv_weights_launch(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin,
+                             cudaStream_t stream);
+int maxpool2_fwd_launch(const float* x, int H, int W, int C, float* y, cudaStream_t stream);
+int maxpool2_bwd_launch(const float* dy, const float* x, int H, int W, int C, int relu_mask,
+                        float* dx, cudaStream_t stream);
+int relu_fwd_launch(const float* x, long n, float* y, cudaStream_t stream);
+int relu_bwd_launch(const float* dy, const float* x, long n, int accumulate, float* dx,
+                    cudaStream_t stream);
+int add_inplace_launch(float* dst, const float* src, long n, cudaStream_t stream);
+int content_fwd_launch(const float* f, const float* t, long n, float* partials, float* loss_out,
+                       cudaStream_t stream);
+int content_bwd_launch(const float* f, const float* t, long n, const float* grad_w, int accumulate,
+                       float* df, cudaStream_t stream);
+int adam_step_launch(float* x, const float* g, float* m, float* v, long n, float beta1, float beta2,
+                     float eps, float step_size, float bias2_sqrt, cudaStream_t stream);
+int adam_step_dev_launch(float* x, const float* g, float* m, float* v, long n, float lr, float beta1,
+                         float beta2, float eps, float* state, cudaStream_t stream);
+int reduce_scratch_floats();
+int dot_launch(const float* a, const float* b, long n, float* partials, float* out,
+               cudaStream_t stream);
+int absmax_sum_launch(const float* a, long n, float* partials, float* out2, cudaStream_t stream);
+int axpy_launch(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
+                cudaStream_t stream);
+int scale_launch(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
+                 cudaStream_t stream);
+int frame_to_u8_launch(const float* img_nchw, int H, int W, int denormalize, int rounding,
+                       unsigned char* out_hwc, cudaStream_t stream);
+int nchw_to_nhwc_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);
+int nhwc_to_nchw_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);
+int finite_flags_launch(const float* vals, int n, int* flags, cudaStream_t stream);
+
+}  // namespace stv

@@ -1,0 +1,219 @@
+"""Tensor-level wrappers over the C-ABI kernels (one Python function per entry point).
+
+All functions enqueue on torch's current CUDA stream and never synchronise, so sequences of them
+can be captured into a CUDA graph.  Activations are NHWC fp32 tensors of shape ``[H, W, C]``; the
+image and its gradient are NCHW ``[1, 3, H, W]`` as in the reference.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nat
+
+GRAM_MATRIX_CLAMP_MAX = 5e5  # reference constants.py:15
+
+
+def _chk(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        msg = f"{name}: expected a contiguous fp32 CUDA tensor, got {t.dtype} on {t.device}"
+        raise ValueError(msg)
+
+
+def _s(t: torch.Tensor) -> int:
+    return nat.stream_ptr(t.device)
+
+
+def pack_conv_weights(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """torch ``[Cout, Cin, 3, 3]`` -> (fwd ``[9, Cout, Cin]``, dgrad ``[9, Cin, Cout]`` flipped)."""
+    _chk(w, "w")
+    cout, cin = w.shape[0], w.shape[1]
+    wf = torch.empty(9, cout, cin, device=w.device, dtype=torch.float32)
+    wd = torch.empty(9, cin, cout, device=w.device, dtype=torch.float32)
+    nat.call("stv_pack_conv_weights", nat.ptr(w), nat.ptr(wf), nat.ptr(wd), cout, cin, _s(w))
+    return wf, wd
+
+
+def conv3x3_first_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
+                      out_pre: torch.Tensor | None, out_post: torch.Tensor | None) -> None:
+    _chk(img, "img")
+    h, wd = img.shape[-2], img.shape[-1]
+    nat.call("stv_conv3x3_first_fwd", nat.ptr(img), nat.ptr(w), nat.ptr(bias), h, wd, w.shape[0],
+             nat.ptr(out_pre), nat.ptr(out_post), _s(img))
+
+
+def conv3x3_fwd(x: torch.Tensor, w_fwd: torch.Tensor, bias: torch.Tensor | None,
+                out_pre: torch.Tensor | None, out_post: torch.Tensor | None) -> None:
+    _chk(x, "x")
+    h, wd, cin = x.shape
+    cout = w_fwd.shape[1]
+    nat.call("stv_conv3x3_fwd", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
+             nat.ptr(out_pre), nat.ptr(out_post), _s(x))
+
+
+def conv3x3_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, dx: torch.Tensor,
+                  relu_src: torch.Tensor | None = None, *, accumulate: bool = False) -> None:
+    _chk(dy, "dy")
+    h, wd, cout = dy.shape
+    cin = w_dgrad.shape[1]
+    nat.call("stv_conv3x3_dgrad", nat.ptr(dy), nat.ptr(w_dgrad), h, wd, cout, cin,
+             nat.ptr(relu_src), int(accumulate), nat.ptr(dx), _s(dy))
+
+
+def conv3x3_first_dgrad(dy: torch.Tensor, w: torch.Tensor, dimg: torch.Tensor) -> None:
+    _chk(dy, "dy")
+    h, wd, cout = dy.shape
+    nat.call("stv_conv3x3_first_dgrad", nat.ptr(dy), nat.ptr(w), h, wd, cout, nat.ptr(dimg),
+             _s(dy))
+
+
+def maxpool2_fwd(x: torch.Tensor, y: torch.Tensor) -> None:
+    _chk(x, "x")
+    h, wd, c = x.shape
+    nat.call("stv_maxpool2_fwd", nat.ptr(x), h, wd, c, nat.ptr(y), _s(x))
+
+
+def maxpool2_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, *, relu_mask: bool) -> None:
+    _chk(dy, "dy")
+    h, wd, c = x.shape
+    nat.call("stv_maxpool2_bwd", nat.ptr(dy), nat.ptr(x), h, wd, c, int(relu_mask), nat.ptr(dx),
+             _s(x))
+
+
+def relu_fwd(x: torch.Tensor, y: torch.Tensor) -> None:
+    nat.call("stv_relu_fwd", nat.ptr(x), x.numel(), nat.ptr(y), _s(x))
+
+
+def relu_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, *, accumulate: bool) -> None:
+    nat.call("stv_relu_bwd", nat.ptr(dy), nat.ptr(x), x.numel(), int(accumulate), nat.ptr(dx),
+             _s(x))
+
+
+def add_inplace(dst: torch.Tensor, src: torch.Tensor) -> None:
+    nat.call("stv_add_inplace", nat.ptr(dst), nat.ptr(src), dst.numel(), _s(dst))
+
+
+def gram_workspace(hw: int, channels: int, device: torch.device) -> torch.Tensor:
+    nbytes = nat.gram_workspace_bytes(hw, channels)
+    return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32)
+
+
+def gram_loss_fwd(x: torch.Tensor, workspace: torch.Tensor, *, target: torch.Tensor | None = None,
+                  gram_out: torch.Tensor | None = None, s_out: torch.Tensor | None = None,
+                  loss_out: torch.Tensor | None = None,
+                  clamp_max: float = GRAM_MATRIX_CLAMP_MAX) -> None:
+    """x: ``[H, W, C]`` (or ``[HW, C]``) features.  See ``stv_gram_loss_fwd``."""
+    _chk(x, "x")
+    c = x.shape[-1]
+    hw = x.numel() // c
+    nat.call("stv_gram_loss_fwd", nat.ptr(x), hw, c, nat.ptr(workspace), workspace.numel() * 4,
+             nat.ptr(target), float(clamp_max), nat.ptr(gram_out), nat.ptr(s_out),
+             nat.ptr(loss_out), _s(x))
+
+
+def style_bwd(x: torch.Tensor, s: torch.Tensor, grad_w: torch.Tensor, dy: torch.Tensor, *,
+              accumulate: bool) -> None:
+    c = x.shape[-1]
+    hw = x.numel() // c
+    nat.call("stv_style_bwd", nat.ptr(x), nat.ptr(s), hw, c, nat.ptr(grad_w), int(accumulate),
+             nat.ptr(dy), _s(x))
+
+
+def content_loss_fwd(f: torch.Tensor, t: torch.Tensor, partials: torch.Tensor,
+                     loss_out: torch.Tensor) -> None:
+    nat.call("stv_content_loss_fwd", nat.ptr(f), nat.ptr(t), f.numel(), nat.ptr(partials),
+             nat.ptr(loss_out), _s(f))
+
+
+def content_loss_bwd(f: torch.Tensor, t: torch.Tensor, grad_w: torch.Tensor, df: torch.Tensor, *,
+                     accumulate: bool) -> None:
+    nat.call("stv_content_loss_bwd", nat.ptr(f), nat.ptr(t), f.numel(), nat.ptr(grad_w),
+             int(accumulate), nat.ptr(df), _s(f))
+
+
+def adam_step(x: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, beta1: float,
+              beta2: float, eps: float, step_size: float, bias2_sqrt: float) -> None:
+    nat.call("stv_adam_step", nat.ptr(x), nat.ptr(g), nat.ptr(m), nat.ptr(v), x.numel(), beta1,
+             beta2, eps, step_size, bias2_sqrt, _s(x))
+
+
+def adam_step_dev(x: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor,
+                  state3: torch.Tensor, *, lr: float, beta1: float, beta2: float,
+                  eps: float) -> None:
+    nat.call("stv_adam_step_dev", nat.ptr(x), nat.ptr(g), nat.ptr(m), nat.ptr(v), x.numel(), lr,
+             beta1, beta2, eps, nat.ptr(state3), _s(x))
+
+
+def dot(a: torch.Tensor, b: torch.Tensor, partials: torch.Tensor, out: torch.Tensor) -> None:
+    nat.call("stv_dot", nat.ptr(a), nat.ptr(b), a.numel(), nat.ptr(partials), nat.ptr(out), _s(a))
+
+
+def absmax_sum(a: torch.Tensor, partials: torch.Tensor, out2: torch.Tensor) -> None:
+    nat.call("stv_absmax_sum", nat.ptr(a), a.numel(), nat.ptr(partials), nat.ptr(out2), _s(a))
+
+
+def axpy(alpha: float | torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> None:
+    """y += alpha * x (alpha: host float or 0-dim/1-elem device tensor)."""
+    if isinstance(alpha, torch.Tensor):
+        nat.call("stv_axpy", nat.ptr(alpha), 0.0, nat.ptr(x), nat.ptr(y), x.numel(), _s(x))
+    else:
+        nat.call("stv_axpy", None, float(alpha), nat.ptr(x), nat.ptr(y), x.numel(), _s(x))
+
+
+def scale(alpha: float | torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> None:
+    """y = alpha * x."""
+    if isinstance(alpha, torch.Tensor):
+        nat.call("stv_scale", nat.ptr(alpha), 0.0, nat.ptr(x), nat.ptr(y), x.numel(), _s(x))
+    else:
+        nat.call("stv_scale", None, float(alpha), nat.ptr(x), nat.ptr(y), x.numel(), _s(x))
+
+
+def frame_to_u8(img: torch.Tensor, out: torch.Tensor, *, denormalize: bool,
+                rounding: bool = False) -> None:
+    """img ``[1,3,H,W]`` fp32 -> out ``[H,W,3]`` uint8 (device)."""
+    h, wd = img.shape[-2], img.shape[-1]
+    nat.call("stv_frame_to_u8", nat.ptr(img), h, wd, int(denormalize), int(rounding),
+             nat.ptr(out), _s(img))
+
+
+def nchw_to_nhwc(src: torch.Tensor) -> torch.Tensor:
+    """``[1,C,H,W]`` or ``[C,H,W]`` -> ``[H,W,C]`` (copy)."""
+    c, h, wd = src.shape[-3], src.shape[-2], src.shape[-1]
+    dst = torch.empty(h, wd, c, device=src.device, dtype=torch.float32)
+    nat.call("stv_nchw_to_nhwc", nat.ptr(src), c, h, wd, nat.ptr(dst), _s(src))
+    return dst
+
+
+def nhwc_to_nchw(src: torch.Tensor) -> torch.Tensor:
+    """``[H,W,C]`` -> ``[1,C,H,W]`` (copy)."""
+    h, wd, c = src.shape
+    dst = torch.empty(1, c, h, wd, device=src.device, dtype=torch.float32)
+    nat.call("stv_nhwc_to_nchw", nat.ptr(src), c, h, wd, nat.ptr(dst), _s(src))
+    return dst
+
+
+def finite_flags(vals: torch.Tensor, flags: torch.Tensor) -> None:
+    nat.call("stv_finite_flags", nat.ptr(vals), vals.numel(), nat.ptr(flags), _s(vals))
+
+
+def conv_igemm_ex(x: torch.Tensor, w_packed: torch.Tensor, *, taps: int,  # noqa: PLR0913
+                  bias: torch.Tensor | None = None, alpha: torch.Tensor | None = None,
+                  mask_src: torch.Tensor | None = None, add_src: torch.Tensor | None = None,
+                  out_pre: torch.Tensor | None = None, out_post: torch.Tensor | None = None,
+                  block_n: int = 0, th: int = 0, tw: int = 0) -> None:
+    """Test hook: the tensor-core conv with explicit tile selection."""
+    h, wd, c = x.shape
+    n = w_packed.shape[-2]
+    nat.call("stv_conv_igemm_ex", nat.ptr(x), nat.ptr(w_packed), h, wd, c, n, taps, nat.ptr(bias),
+             nat.ptr(alpha), nat.ptr(mask_src), nat.ptr(add_src), nat.ptr(out_pre),
+             nat.ptr(out_post), block_n, th, tw, _s(x))
+
+
+def conv_ref(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None, *, taps: int,
+             relu: bool) -> torch.Tensor:
+    """Test hook: naive CUDA-core conv with the same packed weights."""
+    h, wd, c = x.shape
+    n = w_packed.shape[-2]
+    out = torch.empty(h, wd, n, device=x.device, dtype=torch.float32)
+    nat.call("stv_conv_ref", nat.ptr(x), nat.ptr(w_packed), nat.ptr(bias), h, wd, c, n, taps,
+             int(relu), nat.ptr(out), _s(x))
+    return out

@@ -1,0 +1,481 @@
+"""Kernel-level self-test on a real B200: every C-ABI kernel against plain PyTorch fp32.
+
+Each case runs in its own subprocess (own CUDA context, own timeout) so a trapping kernel cannot
+take the remaining cases down.  Usage (on the GPU box):
+    python tools/gpu_selftest.py [--cases a,b,...] [--out gpurun_out/selftest.log]
+"""
+from __future__ import annotations
+
+import argparse
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+CASES = ["elementwise", "conv", "conv_variants", "gram", "perf"]
+
+
+def rel_l2(a, b):  # noqa: ANN001, ANN201
+    import torch
+
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float(torch.linalg.vector_norm(a - b) / (torch.linalg.vector_norm(b) + 1e-300))
+
+
+def report(name: str, err: float, tol: float, extra: str = "") -> bool:
+    ok = err <= tol and err == err  # noqa: PLR0124
+    print(f"{'PASS' if ok else 'FAIL'}  {name:<58s} err={err:.3e} tol={tol:.1e} {extra}", flush=True)
+    return ok
+
+
+def nhwc(t):  # noqa: ANN001, ANN201
+    """[1,C,H,W] -> contiguous [H,W,C]."""
+    return t[0].permute(1, 2, 0).contiguous()
+
+
+def case_elementwise() -> bool:
+    import torch
+    import torch.nn.functional as F  # noqa: N812
+
+    from style_transfer_visualizer_b200 import _native as nat
+    from style_transfer_visualizer_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    nat.require_device(dev)
+    ok = True
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    # pack weights
+    w = torch.randn(128, 64, 3, 3, device=dev, generator=g)
+    wf, wd = ops.pack_conv_weights(w)
+    ok &= report("pack fwd", rel_l2(wf, w.permute(2, 3, 0, 1).reshape(9, 128, 64)), 0)
+    ok &= report("pack dgrad", rel_l2(wd, w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 64, 128)), 0)
+
+    for (h, wdt) in [(64, 64), (33, 47), (135, 250)]:
+        # first conv fwd
+        img = torch.randn(1, 3, h, wdt, device=dev, generator=g)
+        w1 = torch.randn(64, 3, 3, 3, device=dev, generator=g) * 0.2
+        b1 = torch.randn(64, device=dev, generator=g)
+        pre = torch.empty(h, wdt, 64, device=dev)
+        post = torch.empty_like(pre)
+        ops.conv3x3_first_fwd(img, w1, b1, pre, post)
+        ref = F.conv2d(img, w1, b1, padding=1)
+        ok &= report(f"conv_first_fwd pre {h}x{wdt}", rel_l2(pre, nhwc(ref)), 2e-6)
+        ok &= report(f"conv_first_fwd post {h}x{wdt}", rel_l2(post, nhwc(ref.relu())), 2e-6)
+        # first conv dgrad
+        dy = torch.randn(1, 64, h, wdt, device=dev, generator=g)
+        dimg = torch.empty(1, 3, h, wdt, device=dev)
+        ops.conv3x3_first_dgrad(nhwc(dy), w1, dimg)
+        refd = torch.nn.grad.conv2d_input(img.shape, w1, dy, padding=1)
+        ok &= report(f"conv_first_dgrad {h}x{wdt}", rel_l2(dimg, refd), 2e-6)
+        # pool fwd / bwd
+        x = torch.randn(1, 64, h, wdt, device=dev, generator=g).relu().requires_grad_(True)
+        y = F.max_pool2d(x, 2, 2)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        yo = torch.empty(h // 2, wdt // 2, 64, device=dev)
+        ops.maxpool2_fwd(nhwc(x.detach()), yo)
+        ok &= report(f"maxpool fwd {h}x{wdt}", rel_l2(yo, nhwc(y.detach())), 0)
+        dxo = torch.full((h, wdt, 64), 7.0, device=dev)
+        ops.maxpool2_bwd(nhwc(gy), nhwc(x.detach()), dxo, relu_mask=False)
+        ok &= report(f"maxpool bwd {h}x{wdt}", rel_l2(dxo, nhwc(x.grad)), 0)
+        # fused relu gate: x is post-ReLU -> same as autograd through relu(max_pool)
+        xr = torch.randn(1, 64, h, wdt, device=dev, generator=g).requires_grad_(True)
+        yr = F.max_pool2d(xr.relu(), 2, 2)
+        yr.backward(gy)
+        ops.maxpool2_bwd(nhwc(gy), nhwc(xr.detach().relu()), dxo, relu_mask=True)
+        ok &= report(f"maxpool+relu bwd {h}x{wdt}", rel_l2(dxo, nhwc(xr.grad)), 0)
+
+    # relu
+    x = torch.randn(4096 * 4, device=dev, generator=g)
+    y = torch.empty_like(x)
+    ops.relu_fwd(x, y)
+    ok &= report("relu fwd", rel_l2(y, x.relu()), 0)
+    dy = torch.randn_like(x)
+    dx = torch.ones_like(x)
+    ops.relu_bwd(dy, x, dx, accumulate=True)
+    ok &= report("relu bwd acc", rel_l2(dx, 1 + dy * (x > 0)), 0)
+
+    # content loss
+    n = 512 * 33 * 47
+    f = torch.randn(n, device=dev, generator=g)
+    t = torch.randn(n, device=dev, generator=g)
+    part = torch.empty(nat.reduce_scratch_floats() * 2, device=dev)
+    loss = torch.zeros(1, device=dev)
+    ops.content_loss_fwd(f, t, part, loss)
+    ok &= report("content fwd", abs(float(loss) - float(F.mse_loss(f.double(), t.double())))
+                 / float(F.mse_loss(f.double(), t.double())), 1e-6)
+    gw = torch.tensor([3.0], device=dev)
+    df = torch.empty_like(f)
+    ops.content_loss_bwd(f, t, gw, df, accumulate=False)
+    ok &= report("content bwd", rel_l2(df, 3.0 * 2 * (f - t) / n), 1e-6)
+
+    # adam vs torch.optim.Adam
+    p = torch.randn(100003, device=dev, generator=g)
+    p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=0.01)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    p_dev = p.clone()
+    m2 = torch.zeros_like(p)
+    v2 = torch.zeros_like(p)
+    state = torch.zeros(3, device=dev)
+    for step in range(1, 6):
+        grad = torch.randn(p.shape, device=dev, generator=g)
+        p_ref.grad = grad.clone()
+        opt.step()
+        bc1 = 1 - 0.9 ** step
+        bc2 = 1 - 0.999 ** step
+        ops.adam_step(p, grad, m, v, beta1=0.9, beta2=0.999, eps=1e-8, step_size=0.01 / bc1,
+                      bias2_sqrt=bc2 ** 0.5)
+        ops.adam_step_dev(p_dev, grad, m2, v2, state, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8)
+    ok &= report("adam 5 steps", rel_l2(p, p_ref.detach()), 1e-6)
+    ok &= report("adam_dev 5 steps", rel_l2(p_dev, p_ref.detach()), 1e-6)
+
+    # dot / absmax / axpy / scale
+    a = torch.randn(1000003, device=dev, generator=g)
+    b = torch.randn(1000003, device=dev, generator=g)
+    out = torch.zeros(2, device=dev)
+    ops.dot(a, b, part, out[:1])
+    ok &= report("dot", abs(float(out[0]) - float(a.double() @ b.double())) / float(a.norm() * b.norm()), 1e-6)
+    ops.absmax_sum(a, part, out)
+    ok &= report("absmax", abs(float(out[0]) - float(a.abs().max())), 0)
+    ok &= report("abssum", abs(float(out[1]) - float(a.double().abs().sum())) / float(a.double().abs().sum()), 1e-6)
+    yv = b.clone()
+    ops.axpy(0.5, a, yv)
+    ok &= report("axpy host", rel_l2(yv, b + 0.5 * a), 1e-7)
+    yv = b.clone()
+    ops.axpy(torch.tensor([-2.0], device=dev), a, yv)
+    ok &= report("axpy dev", rel_l2(yv, b - 2.0 * a), 1e-7)
+    ops.scale(3.0, a, yv)
+    ok &= report("scale", rel_l2(yv, 3.0 * a), 0)
+
+    # frame conversion (bit exact vs the reference's torch+numpy arithmetic)
+    for (h, wdt) in [(64, 64), (33, 47)]:
+        img = torch.randn(1, 3, h, wdt, device=dev, generator=g) * 2
+        img[0, 0, 0, 0] = float("nan")
+        img[0, 1, 0, 1] = float("inf")
+        img[0, 2, 0, 2] = float("-inf")
+        for denorm in (True, False):
+            mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
+            std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
+            t_ = img * std + mean if denorm else img
+            t_ = torch.nan_to_num(t_, nan=0.0, posinf=1.0, neginf=0.0).clamp(0, 1)
+            ref_np = (t_.squeeze(0).permute(1, 2, 0).cpu().numpy() * 255).astype("uint8")
+            out8 = torch.empty(h, wdt, 3, device=dev, dtype=torch.uint8)
+            ops.frame_to_u8(img, out8, denormalize=denorm)
+            diff = int((out8.cpu().numpy().astype(int) - ref_np.astype(int)).__abs__().max())
+            ok &= report(f"frame_to_u8 {h}x{wdt} denorm={denorm}", float(diff), 0)
+
+    # layout
+    t4 = torch.randn(1, 64, 33, 47, device=dev, generator=g)
+    ok &= report("nchw_to_nhwc", rel_l2(ops.nchw_to_nhwc(t4), nhwc(t4)), 0)
+    ok &= report("nhwc_to_nchw", rel_l2(ops.nhwc_to_nchw(nhwc(t4)), t4), 0)
+    vals = torch.tensor([1.0, float("nan"), float("inf"), 0.0], device=dev)
+    flags = torch.zeros(4, device=dev, dtype=torch.int32)
+    ops.finite_flags(vals, flags)
+    ok &= report("finite_flags", float((flags.cpu() != torch.tensor([0, 1, 1, 0])).sum()), 0)
+    torch.cuda.synchronize()
+    return ok
+
+
+def _conv_inputs(h, w, cin, cout, g, dev):  # noqa: ANN001, ANN202, PLR0913
+    import torch
+
+    x = torch.randn(1, cin, h, w, device=dev, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, device=dev, generator=g) * 0.1
+    return x, wt, b
+
+
+def case_conv() -> bool:
+    import torch
+    import torch.nn.functional as F  # noqa: N812
+
+    from style_transfer_visualizer_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ok = True
+    # sanity of the on-device naive conv first (fp32 exact-ish)
+    x, wt, b = _conv_inputs(20, 24, 64, 64, g, dev)
+    wf, wd = ops.pack_conv_weights(wt)
+    ref = nhwc(F.conv2d(x, wt, b, padding=1))
+    ok &= report("conv_ref vs torch", rel_l2(ops.conv_ref(nhwc(x), wf, b, taps=9, relu=False), ref), 1e-6)
+
+    configs = [
+        # h, w, cin, cout, block_n, th, tw
+        (16, 16, 64, 64, 64, 8, 16),
+        (16, 16, 32, 64, 64, 8, 16),
+        (32, 32, 64, 128, 128, 8, 16),
+        (32, 32, 128, 256, 256, 8, 16),
+        (24, 40, 64, 64, 64, 4, 32),
+        (24, 40, 64, 64, 64, 16, 8),
+        (8, 128, 64, 64, 64, 1, 128),
+        (10, 70, 64, 64, 64, 2, 64),
+        (33, 47, 128, 128, 128, 8, 16),   # ragged edges
+        (67, 120, 512, 512, 256, 16, 8),  # conv5_1 @1080p
+        (67, 120, 512, 512, 128, 0, 0),   # auto patch
+        (135, 240, 256, 512, 0, 0, 0),    # all auto
+        (64, 64, 512, 512, 64, 0, 0),
+    ]
+    for (h, w, cin, cout, bn, th, tw) in configs:
+        x, wt, b = _conv_inputs(h, w, cin, cout, g, dev)
+        wf, wd = ops.pack_conv_weights(wt)
+        ref = nhwc(F.conv2d(x, wt, b, padding=1))
+        pre = torch.full((h, w, cout), float("nan"), device=dev)
+        post = torch.full((h, w, cout), float("nan"), device=dev)
+        ops.conv_igemm_ex(nhwc(x), wf, taps=9, bias=b, out_pre=pre, out_post=post, block_n=bn,
+                          th=th, tw=tw)
+        torch.cuda.synchronize()
+        tag = f"{h}x{w} {cin}->{cout} bn={bn} patch={th}x{tw}"
+        ok &= report(f"igemm fwd pre  {tag}", rel_l2(pre, ref), 2e-3)
+        ok &= report(f"igemm fwd post {tag}", rel_l2(post, ref.relu()), 2e-3)
+        # dgrad through the same kernel with the flipped/transposed packing
+        dy = torch.randn(1, cout, h, w, device=dev, generator=g)
+        refd = nhwc(torch.nn.grad.conv2d_input(x.shape, wt, dy, padding=1))
+        dx = torch.full((h, w, cin), float("nan"), device=dev)
+        if cin % 64 == 0:
+            ops.conv3x3_dgrad(nhwc(dy), wd, dx)
+            torch.cuda.synchronize()
+            ok &= report(f"igemm dgrad    {tag}", rel_l2(dx, refd), 2e-3)
+    return ok
+
+
+def case_conv_variants() -> bool:
+    import torch
+    import torch.nn.functional as F  # noqa: N812
+
+    from style_transfer_visualizer_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ok = True
+    h, w, cin, cout = 37, 53, 128, 64
+    x, wt, b = _conv_inputs(h, w, cin, cout, g, dev)
+    wf, wd = ops.pack_conv_weights(wt)
+    dy = torch.randn(1, cout, h, w, device=dev, generator=g)
+    act = torch.randn(h, w, cin, device=dev, generator=g)  # stand-in for the saved activation
+    prev = torch.randn(h, w, cin, device=dev, generator=g)
+    refd = nhwc(torch.nn.grad.conv2d_input(x.shape, wt, dy, padding=1))
+    dx = prev.clone()
+    ops.conv3x3_dgrad(nhwc(dy), wd, dx, relu_src=act, accumulate=True)
+    ok &= report("dgrad + relu gate + accumulate", rel_l2(dx, refd * (act > 0) + prev), 2e-3)
+    dx2 = torch.empty_like(prev)
+    ops.conv3x3_dgrad(nhwc(dy), wd, dx2, relu_src=act)
+    ok &= report("dgrad + relu gate", rel_l2(dx2, refd * (act > 0)), 2e-3)
+
+    # 1x1 with alpha (style backward): dy = gw * X @ S
+    for c in (64, 128, 256, 512):
+        hw = 33 * 47
+        xf = torch.randn(hw, c, device=dev, generator=g)
+        s = torch.randn(c, c, device=dev, generator=g)
+        s = (s + s.t()) * 0.5
+        gw = torch.tensor([1e5], device=dev)
+        out = torch.randn(hw, c, device=dev, generator=g)
+        base = out.clone()
+        ops.style_bwd(xf, s, gw, out, accumulate=True)
+        ref = base + 1e5 * (xf.double() @ s.double()).float()
+        ok &= report(f"style_bwd C={c} accumulate", rel_l2(out, ref), 2e-3)
+        ops.style_bwd(xf, s, gw, out, accumulate=False)
+        ok &= report(f"style_bwd C={c}", rel_l2(out, 1e5 * (xf.double() @ s.double()).float()), 2e-3)
+    torch.cuda.synchronize()
+    return ok
+
+
+def case_gram() -> bool:
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ok = True
+    for (hw, c) in [(64 * 64, 64), (33 * 47, 64), (1, 64), (32 * 32, 128), (33 * 47, 128),
+                    (135 * 240, 256), (67 * 120, 512), (7, 512), (540 * 960, 128)]:
+        x = torch.randn(hw, c, device=dev, generator=g) + 0.3
+        ws = ops.gram_workspace(hw, c, dev)
+        gram = torch.full((c, c), float("nan"), device=dev)
+        ops.gram_loss_fwd(x, ws, gram_out=gram)
+        f64 = x.double().t()
+        r = f64 @ f64.t()
+        ref = r.clamp(max=5e5) / (c * hw)
+        ok &= report(f"gram hw={hw} C={c}", rel_l2(gram, ref), 1e-3)
+        # loss + S against autograd of the reference formula
+        target = (ref * 0.9 + 0.01).float()
+        loss = torch.zeros(1, device=dev)
+        s = torch.full((c, c), float("nan"), device=dev)
+        ops.gram_loss_fwd(x, ws, target=target, s_out=s, loss_out=loss)
+        xa = x.double().requires_grad_(True)
+        fa = xa.t()
+        ga = (fa @ fa.t()).clamp(max=5e5) / (c * hw)
+        la = torch.nn.functional.mse_loss(ga, target.double())
+        la.backward()
+        ok &= report(f"gram loss hw={hw} C={c}", abs(float(loss) - float(la)) / float(la), 2e-2)
+        # dX = X @ S
+        ok &= report(f"gram S -> dX hw={hw} C={c}", rel_l2(x.double() @ s.double(), xa.grad), 2e-2)
+    # clamp-active case
+    hw, c = 4096, 128
+    x = torch.randn(hw, c, device=dev, generator=g) * 12 + 3
+    ws = ops.gram_workspace(hw, c, dev)
+    gram = torch.empty(c, c, device=dev)
+    s = torch.empty(c, c, device=dev)
+    loss = torch.zeros(1, device=dev)
+    target = torch.rand(c, c, device=dev, generator=g)
+    ops.gram_loss_fwd(x, ws, target=target, gram_out=gram, s_out=s, loss_out=loss)
+    r = x.double().t() @ x.double()
+    frac = float((r > 5e5).double().mean())
+    # entries within TF32 error of the clamp threshold may legitimately land on either side
+    safe = ((r - 5e5).abs() > 5e5 * 5e-3)
+    ref = r.clamp(max=5e5) / (c * hw)
+    ok &= report(f"gram clamp-active ({frac:.2f} clamped)", rel_l2(gram, ref), 1e-3)
+    sref = 4.0 / (c * c * c * hw) * (r <= 5e5) * (ref - target.double())
+    ok &= report("gram S clamp mask", rel_l2(s.double() * safe, sref * safe), 2e-2)
+    torch.cuda.synchronize()
+    return ok
+
+
+def _time(fn, iters=10, warm=3):  # noqa: ANN001, ANN202
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def case_perf() -> bool:
+    import torch
+    import torch.nn.functional as F  # noqa: N812
+
+    from style_transfer_visualizer_b200 import ops
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(4)
+    layers = [  # 1080p VGG19 conv shapes (H, W, Cin, Cout)
+        (1080, 1920, 64, 64), (540, 960, 64, 128), (540, 960, 128, 128), (270, 480, 128, 256),
+        (270, 480, 256, 256), (135, 240, 256, 512), (135, 240, 512, 512), (67, 120, 512, 512),
+        (512, 512, 64, 64), (256, 256, 128, 128), (128, 128, 256, 256), (64, 64, 512, 512),
+        (32, 32, 512, 512),
+    ]
+    torch.backends.cudnn.allow_tf32 = True
+    for (h, w, cin, cout) in layers:
+        x = torch.randn(h, w, cin, device=dev, generator=g)
+        wt = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * 0.05
+        b = torch.zeros(cout, device=dev)
+        wf, wd = ops.pack_conv_weights(wt)
+        post = torch.empty(h, w, cout, device=dev)
+        flops = 2.0 * 9 * cin * cout * h * w
+        ms = _time(lambda: ops.conv3x3_fwd(x, wf, b, None, post))  # noqa: B023
+        line = f"PERF conv {h}x{w} {cin}->{cout}: auto {ms:.3f} ms {flops / ms / 1e9:.1f} TF/s"
+        for bn in (64, 128, 256):
+            if cout % bn:
+                continue
+            ms2 = _time(lambda: ops.conv_igemm_ex(x, wf, taps=9, bias=b, out_post=post, block_n=bn))  # noqa: B023
+            line += f" | bn{bn} {ms2:.3f} ms {flops / ms2 / 1e9:.1f}"
+        xt = x.permute(2, 0, 1).unsqueeze(0).contiguous(memory_format=torch.channels_last)
+        wcl = wt.contiguous(memory_format=torch.channels_last)
+        ms3 = _time(lambda: F.relu(F.conv2d(xt, wcl, b, padding=1)))  # noqa: B023
+        line += f" | cudnn-tf32 {ms3:.3f} ms {flops / ms3 / 1e9:.1f}"
+        print(line, flush=True)
+    for (hw, c) in [(1080 * 1920, 64), (540 * 960, 128), (270 * 480, 256), (135 * 240, 512),
+                    (67 * 120, 512), (512 * 512, 64), (64 * 64, 512)]:
+        x = torch.randn(hw, c, device=dev, generator=g)
+        ws = ops.gram_workspace(hw, c, dev)
+        tgt = torch.zeros(c, c, device=dev)
+        s = torch.empty(c, c, device=dev)
+        loss = torch.zeros(1, device=dev)
+        ms = _time(lambda: ops.gram_loss_fwd(x, ws, target=tgt, s_out=s, loss_out=loss))  # noqa: B023
+        gb = hw * c * 4 / 1e9
+        xt = x.t().contiguous()
+        ms2 = _time(lambda: torch.mm(xt, xt.t()))  # noqa: B023
+        print(f"PERF gram hw={hw} C={c}: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s  "
+              f"{2.0 * c * c * hw / ms / 1e9:.1f} TF/s(full) | torch.mm fp32 {ms2:.3f} ms", flush=True)
+        gw = torch.ones(1, device=dev)
+        dy = torch.empty(hw, c, device=dev)
+        ms3 = _time(lambda: ops.style_bwd(x, s, gw, dy, accumulate=False))  # noqa: B023
+        print(f"PERF style_bwd hw={hw} C={c}: {ms3:.3f} ms {2.0 * c * c * hw / ms3 / 1e9:.1f} TF/s", flush=True)
+    # memory-bound kernels at 1080p
+    h, w, c = 1080, 1920, 64
+    x = torch.randn(h, w, c, device=dev, generator=g).relu()
+    y = torch.empty(h // 2, w // 2, c, device=dev)
+    ms = _time(lambda: ops.maxpool2_fwd(x, y))
+    print(f"PERF maxpool fwd 1080p C=64: {ms:.3f} ms {(x.numel() + y.numel()) * 4 / ms / 1e6:.0f} GB/s")
+    dx = torch.empty_like(x)
+    ms = _time(lambda: ops.maxpool2_bwd(y, x, dx, relu_mask=True))
+    print(f"PERF maxpool bwd 1080p C=64: {ms:.3f} ms {(2 * x.numel() + y.numel()) * 4 / ms / 1e6:.0f} GB/s")
+    img = torch.randn(1, 3, h, w, device=dev, generator=g)
+    w1 = torch.randn(64, 3, 3, 3, device=dev, generator=g)
+    b1 = torch.zeros(64, device=dev)
+    pre = torch.empty(h, w, 64, device=dev)
+    post = torch.empty(h, w, 64, device=dev)
+    ms = _time(lambda: ops.conv3x3_first_fwd(img, w1, b1, pre, post))
+    print(f"PERF conv_first_fwd 1080p: {ms:.3f} ms {(2 * pre.numel() + img.numel()) * 4 / ms / 1e6:.0f} GB/s")
+    dimg = torch.empty_like(img)
+    ms = _time(lambda: ops.conv3x3_first_dgrad(pre, w1, dimg))
+    print(f"PERF conv_first_dgrad 1080p: {ms:.3f} ms {(pre.numel() + img.numel()) * 4 / ms / 1e6:.0f} GB/s")
+    p = img.flatten().clone()
+    gr = torch.randn_like(p)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    ms = _time(lambda: ops.adam_step(p, gr, m, v, beta1=0.9, beta2=0.999, eps=1e-8, step_size=0.01, bias2_sqrt=1.0))
+    print(f"PERF adam 1080p: {ms:.3f} ms {p.numel() * 28 / ms / 1e6:.0f} GB/s")
+    out8 = torch.empty(h, w, 3, device=dev, dtype=torch.uint8)
+    ms = _time(lambda: ops.frame_to_u8(img, out8, denormalize=True))
+    print(f"PERF frame_to_u8 1080p: {ms:.3f} ms {(img.numel() * 4 + out8.numel()) / ms / 1e6:.0f} GB/s")
+    return True
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default=",".join(CASES))
+    ap.add_argument("--case", default=None, help="internal: run one case in-process")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--timeout", type=int, default=300)
+    args = ap.parse_args()
+    if args.case:
+        ok = globals()[f"case_{args.case}"]()
+        print(f"CASE {args.case}: {'OK' if ok else 'FAILED'}", flush=True)
+        return 0 if ok else 1
+    rc_all = 0
+    out_f = open(args.out, "w") if args.out else None  # noqa: SIM115
+    for case in args.cases.split(","):
+        t0 = time.time()
+        try:
+            proc = subprocess.run([sys.executable, __file__, "--case", case], capture_output=True,
+                                  text=True, timeout=args.timeout, check=False)
+            text = proc.stdout + proc.stderr[-4000:]
+            rc = proc.returncode
+        except subprocess.TimeoutExpired as exc:
+            text = (exc.stdout or b"").decode() if isinstance(exc.stdout, bytes) else (exc.stdout or "")
+            text += f"\nCASE {case}: TIMEOUT after {args.timeout}s\n"
+            rc = 124
+        text += f"[case {case} rc={rc} {time.time() - t0:.1f}s]\n"
+        print(text, flush=True)
+        if out_f:
+            out_f.write(text)
+            out_f.flush()
+        rc_all |= rc
+    return 1 if rc_all else 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
