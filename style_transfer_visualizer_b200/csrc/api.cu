@@ -51,7 +51,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   STV_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   STV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned",
@@ -71,7 +71,9 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
   const CUresult r =
       fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank),
          const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+         swizzle == kSwizzle128B          ? CU_TENSOR_MAP_SWIZZLE_128B
+         : swizzle == kSwizzle128BAtom32B ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                          : CU_TENSOR_MAP_SWIZZLE_NONE,
          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   STV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

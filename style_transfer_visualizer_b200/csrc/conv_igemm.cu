@@ -271,13 +271,13 @@ int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C
     const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)H};
     const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)W * C * 4};
     const uint32_t box[3] = {32, (uint32_t)tw, (uint32_t)th};
-    if (int rc = encode_tmap_f32(&tx, x, 3, dims, strides, box, true)) return rc;
+    if (int rc = encode_tmap_f32(&tx, x, 3, dims, strides, box, kSwizzle128B)) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)C, (uint64_t)taps * N};
     const uint64_t strides[1] = {(uint64_t)C * 4};
     const uint32_t box[2] = {32, (uint32_t)block_n};
-    if (int rc = encode_tmap_f32(&twm, w_packed, 2, dims, strides, box, true)) return rc;
+    if (int rc = encode_tmap_f32(&twm, w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
   }
   ConvIgemmParams p;
   p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.th = th; p.tw = tw; p.tiles_x = tiles_x;

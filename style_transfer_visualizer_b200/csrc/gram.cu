@@ -9,7 +9,8 @@
 //
 // Activations are NHWC, i.e. X[pixel][channel] = F^T, so both MMA operands are "MN-major"
 // (channel contiguous, pixel = K strided): the smem tile written by one TMA box
-// {32 channels, 32 pixels} is consumed directly through an MN-major SWIZZLE_128B descriptor.
+// {32 channels, 32 pixels} (TMA swizzle 128B with 32-byte atoms) is consumed directly through an
+// MN-major SWIZZLE_128B_BASE32B descriptor -- the only swizzled layout valid for MN-major TF32.
 // Work split: (upper-triangle 128x128 block pair) x (pixel range).  Each CTA accumulates its
 // block over its pixel range in TMEM and writes one fp32 partial tile; gram_finalize_kernel sums
 // the partials in a fixed order (deterministic), mirrors, and applies the fused epilogue.
@@ -123,9 +124,10 @@ gram_partial_kernel(const __grid_constant__ CUtensorMap tmap_x, const GramParams
         const uint32_t b_addr = diag ? a_addr : a_addr + kGramOperandBytes;
 #pragma unroll
         for (int k = 0; k < kGramPix / 8; ++k) {
-          // MN-major: 32-channel groups are kGramChunkBytes apart (LBO), 8-pixel K groups 1024 B.
-          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 1024, kGramChunkBytes, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 1024, kGramChunkBytes, 1024);
+          // MN-major TF32 => SWIZZLE_128B_BASE32B: 32-channel groups are kGramChunkBytes apart
+          // (LBO), 4-pixel K groups 512 B apart (SBO); one MMA consumes 8 pixels = 1024 B.
+          const uint64_t adesc = make_smem_desc(a_addr + k * 1024, kGramChunkBytes, 512, 1);
+          const uint64_t bdesc = make_smem_desc(b_addr + k * 1024, kGramChunkBytes, 512, 1);
           umma_tf32(tmem_d, adesc, bdesc, idesc, (it | k) != 0);
         }
         umma_commit(bar_base + 8 * (kGramStages + s));
@@ -304,7 +306,7 @@ int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspa
     const uint64_t dims[2] = {(uint64_t)g.Cv, (uint64_t)g.rows};
     const uint64_t strides[1] = {(uint64_t)g.Cv * 4};
     const uint32_t box[2] = {32, (uint32_t)kGramPix};
-    if (int rc = encode_tmap_f32(&tx, x, 2, dims, strides, box, true)) return rc;
+    if (int rc = encode_tmap_f32(&tx, x, 2, dims, strides, box, kSwizzle128BAtom32B)) return rc;
     GramParams p;
     p.pairs = g.pairs; p.nb = g.nb; p.stages_total = g.stages_total;
     p.stages_per_split = g.stages_per_split; p.partials = partials;

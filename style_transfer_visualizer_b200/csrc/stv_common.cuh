@@ -34,9 +34,10 @@ const char* last_error();
   } while (0)
 
 // Encode a tiled TMA descriptor (fp32 elements). dims/box are innermost-first. strides_bytes has
-// rank-1 entries (stride of dims 1..rank-1). swizzle128 selects CU_TENSOR_MAP_SWIZZLE_128B.
+// rank-1 entries (stride of dims 1..rank-1). swizzle is a TmapSwizzle.
+enum TmapSwizzle { kSwizzleNone = 0, kSwizzle128B = 1, kSwizzle128BAtom32B = 2 };
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 int device_sm_count();
 
@@ -213,6 +214,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   start address / LBO / SBO are stored >>4.  See cute/arch/mma_sm100_desc.hpp for the
 //   bit positions this mirrors (public CUTLASS headers; layout only, no code reuse).
+//   layout_type: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only
+//   swizzled layout the hardware accepts for MN-major TF32 operands).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(layout_type & 7) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
                                                          uint32_t sbo_bytes) {
   uint64_t d = 0;

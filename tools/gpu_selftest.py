@@ -209,7 +209,7 @@ def case_conv() -> bool:
     x, wt, b = _conv_inputs(20, 24, 64, 64, g, dev)
     wf, wd = ops.pack_conv_weights(wt)
     ref = nhwc(F.conv2d(x, wt, b, padding=1))
-    ok &= report("conv_ref vs torch", rel_l2(ops.conv_ref(nhwc(x), wf, b, taps=9, relu=False), ref), 1e-6)
+    ok &= report("conv_ref vs torch", rel_l2(ops.conv_ref(nhwc(x), wf, b, taps=9, relu=False), ref), 5e-6)
 
     configs = [
         # h, w, cin, cout, block_n, th, tw
@@ -311,7 +311,11 @@ def case_gram() -> bool:
         f64 = x.double().t()
         r = f64 @ f64.t()
         ref = r.clamp(max=5e5) / (c * hw)
-        ok &= report(f"gram hw={hw} C={c}", rel_l2(gram, ref), 1e-3)
+        good = report(f"gram hw={hw} C={c}", rel_l2(gram, ref), 1e-3)
+        if not good:
+            print("   got", gram[0, :4].tolist(), gram[c - 1, c - 4:].tolist())
+            print("   ref", ref[0, :4].tolist(), ref[c - 1, c - 4:].tolist())
+        ok &= good
         # loss + S against autograd of the reference formula
         target = (ref * 0.9 + 0.01).float()
         loss = torch.zeros(1, device=dev)
@@ -322,7 +326,7 @@ def case_gram() -> bool:
         ga = (fa @ fa.t()).clamp(max=5e5) / (c * hw)
         la = torch.nn.functional.mse_loss(ga, target.double())
         la.backward()
-        ok &= report(f"gram loss hw={hw} C={c}", abs(float(loss) - float(la)) / float(la), 2e-2)
+        ok &= report(f"gram loss hw={hw} C={c}", abs(float(loss) - float(la.detach())) / float(la.detach()), 2e-2)
         # dX = X @ S
         ok &= report(f"gram S -> dX hw={hw} C={c}", rel_l2(x.double() @ s.double(), xa.grad), 2e-2)
     # clamp-active case
