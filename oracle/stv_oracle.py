@@ -229,8 +229,8 @@ def run(model, x: torch.Tensor, optimizer: torch.optim.Optimizer, steps: int, *,
         last[:] = [s, c, t]
         if res.first_grad is None:
             res.first_grad = x.grad.detach().clone()
-            res.layer_style = [float(v) for v in sl]
-            res.layer_content = [float(v) for v in cl]
+            res.layer_style = [float(v.detach()) for v in sl]
+            res.layer_content = [float(v.detach()) for v in cl]
         return t
 
     t0 = time.perf_counter()

@@ -1,0 +1,375 @@
+"""Execution engine: the truncated VGG19 feature stack, its losses and their input gradient as a
+fixed program of sm_100a kernels over preallocated NHWC workspaces.
+
+This is what runs underneath ``StyleContentModel.forward`` / ``loss.backward()`` (reference
+core_model.py:297-328 and optimization.py:292,313).  The layer list is fused into *stages*
+``conv [-> relu [-> pool]]``; ReLU is applied in the producing conv's epilogue (dual pre/post
+outputs where a loss taps the pre-activation), the ReLU backward mask is applied in the epilogue
+of the *next* layer's dgrad, and the loss gradients are accumulated in place into the tapped
+layer's gradient buffer.  Any tap position the reference allows (conv, ReLU or pool outputs) is
+supported; non-default positions take a few extra memory-bound passes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+from torch import nn
+
+from . import _native as nat
+from . import ops
+
+
+@dataclass
+class _Stage:
+    conv_idx: int
+    cin: int
+    cout: int
+    weight: torch.Tensor            # torch layout [Cout, Cin, 3, 3]
+    bias: torch.Tensor | None
+    relu_idx: int | None = None     # index of the ReLU fused into this stage (None: out of range)
+    pool_idx: int | None = None
+    w_fwd: torch.Tensor | None = None
+    w_dgrad: torch.Tensor | None = None
+
+
+@dataclass
+class _Workspace:
+    """All device buffers of one image size; reused every step (CUDA-graph friendly)."""
+
+    height: int
+    width: int
+    hw: list[tuple[int, int]] = field(default_factory=list)       # conv spatial size per stage
+    pre: list[torch.Tensor | None] = field(default_factory=list)
+    post: list[torch.Tensor | None] = field(default_factory=list)
+    pool: list[torch.Tensor | None] = field(default_factory=list)
+    d_y: list[torch.Tensor | None] = field(default_factory=list)
+    d_post: list[torch.Tensor | None] = field(default_factory=list)
+    d_pool: list[torch.Tensor | None] = field(default_factory=list)
+    gram_ws: list[torch.Tensor] = field(default_factory=list)
+    s_mat: list[torch.Tensor] = field(default_factory=list)
+    losses: torch.Tensor | None = None
+    scratch: torch.Tensor | None = None
+    grad_img: torch.Tensor | None = None
+    generation: int = 0
+    nbytes: int = 0
+
+
+class VggLossEngine:
+    """Runs forward losses / input gradient for one model (weights + tap sets) on one device."""
+
+    def __init__(self, layers: list[nn.Module], style_idx: list[int], content_idx: list[int],
+                 device: torch.device) -> None:
+        nat.require_device(device)
+        self.device = device
+        self.style_idx = sorted(set(style_idx))
+        self.content_idx = sorted(set(content_idx))
+        self._tapped = set(self.style_idx) | set(self.content_idx)
+        self.stages = self._build_stages(layers)
+        self._workspaces: dict[tuple[int, int], _Workspace] = {}
+        self.style_targets: list[torch.Tensor] | None = None          # [C, C] each
+        self.content_targets_nhwc: list[torch.Tensor] | None = None   # [h, w, C] each
+        self.kernel_launches_fwd = 0
+        self.kernel_launches_bwd = 0
+
+    # ------------------------------------------------------------------ program construction
+    def _build_stages(self, layers: list[nn.Module]) -> list[_Stage]:
+        stages: list[_Stage] = []
+        i = 0
+        n = len(layers)
+        while i < n:
+            layer = layers[i]
+            if not isinstance(layer, nn.Conv2d):
+                msg = f"layer {i}: expected Conv2d to start a stage, found {type(layer).__name__}"
+                raise TypeError(msg)
+            if layer.kernel_size != (3, 3) or layer.padding != (1, 1) or layer.stride != (1, 1):
+                msg = f"layer {i}: only 3x3 / stride 1 / pad 1 convolutions are supported"
+                raise ValueError(msg)
+            w = layer.weight.detach().to(self.device, torch.float32).contiguous()
+            b = None if layer.bias is None else \
+                layer.bias.detach().to(self.device, torch.float32).contiguous()
+            st = _Stage(conv_idx=i, cin=w.shape[1], cout=w.shape[0], weight=w, bias=b)
+            i += 1
+            if i < n and isinstance(layers[i], nn.ReLU):
+                st.relu_idx = i
+                i += 1
+                if i < n and isinstance(layers[i], nn.MaxPool2d):
+                    pool = layers[i]
+                    ks = pool.kernel_size if isinstance(pool.kernel_size, tuple) \
+                        else (pool.kernel_size,) * 2
+                    sd = pool.stride if isinstance(pool.stride, tuple) else (pool.stride,) * 2
+                    if ks != (2, 2) or sd != (2, 2) or pool.ceil_mode:
+                        msg = f"layer {i}: only MaxPool2d(2, 2) floor-mode is supported"
+                        raise ValueError(msg)
+                    st.pool_idx = i
+                    i += 1
+            elif i < n:
+                msg = f"layer {i}: a convolution must be followed by ReLU in this network"
+                raise TypeError(msg)
+            stages.append(st)
+        if not stages:
+            msg = "no layers to run: style/content layer indices select nothing"
+            raise ValueError(msg)
+        first = stages[0]
+        if first.cin != 3 or first.cout != 64:
+            msg = f"first convolution must be 3->64 channels (got {first.cin}->{first.cout})"
+            raise ValueError(msg)
+        for st in stages[1:]:
+            if st.cin % 64 or st.cout % 64:
+                msg = (f"layer {st.conv_idx}: tensor-core conv needs channel counts that are "
+                       f"multiples of 64 (got {st.cin}->{st.cout})")
+                raise ValueError(msg)
+            st.w_fwd, st.w_dgrad = ops.pack_conv_weights(st.weight)
+        return stages
+
+    def _out_hw(self, height: int, width: int) -> list[tuple[int, int]]:
+        sizes = []
+        h, w = height, width
+        for st in self.stages:
+            sizes.append((h, w))
+            if st.pool_idx is not None:
+                h, w = h // 2, w // 2
+                if h < 1 or w < 1:
+                    msg = f"image {height}x{width} is too small for the pooling depth"
+                    raise ValueError(msg)
+        return sizes
+
+    def _workspace(self, height: int, width: int, *, with_grad: bool) -> _Workspace:
+        key = (height, width)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = _Workspace(height=height, width=width)
+            ws.hw = self._out_hw(height, width)
+            dev = self.device
+
+            def buf(*shape: int) -> torch.Tensor:
+                t = torch.empty(*shape, device=dev, dtype=torch.float32)
+                ws.nbytes += t.numel() * 4
+                return t
+
+            for st, (h, w) in zip(self.stages, ws.hw):
+                need_pre = st.conv_idx in self._tapped or st.relu_idx is None
+                ws.pre.append(buf(h, w, st.cout) if need_pre else None)
+                ws.post.append(buf(h, w, st.cout) if st.relu_idx is not None else None)
+                ws.pool.append(buf(h // 2, w // 2, st.cout) if st.pool_idx is not None else None)
+                ws.d_y.append(None)
+                ws.d_post.append(None)
+                ws.d_pool.append(None)
+            for idx in self.style_idx:
+                t = self._tap_tensor(ws, idx)
+                c = t.shape[-1]
+                ws.gram_ws.append(ops.gram_workspace(t.shape[0] * t.shape[1], c, dev))
+                ws.s_mat.append(buf(c, c))
+            ws.losses = torch.zeros(len(self.style_idx) + len(self.content_idx), device=dev,
+                                    dtype=torch.float32)
+            ws.scratch = buf(2 * nat.reduce_scratch_floats())
+            self._workspaces[key] = ws
+        if with_grad and ws.grad_img is None:
+            dev = self.device
+            for s, (st, (h, w)) in enumerate(zip(self.stages, ws.hw)):
+                ws.d_y[s] = torch.empty(h, w, st.cout, device=dev, dtype=torch.float32)
+                ws.nbytes += ws.d_y[s].numel() * 4
+                if st.pool_idx is not None:
+                    ws.d_pool[s] = torch.empty(h // 2, w // 2, st.cout, device=dev,
+                                               dtype=torch.float32)
+                if st.relu_idx is not None and st.relu_idx in self._tapped:
+                    ws.d_post[s] = torch.empty(h, w, st.cout, device=dev, dtype=torch.float32)
+            ws.grad_img = torch.empty(1, 3, height, width, device=dev, dtype=torch.float32)
+        return ws
+
+    def grad_buffer(self, height: int, width: int) -> torch.Tensor:
+        """The NCHW buffer ``backward_losses`` writes for this image size."""
+        return self._workspace(height, width, with_grad=True).grad_img
+
+    def generation_of(self, height: int, width: int) -> int:
+        ws = self._workspaces.get((height, width))
+        return ws.generation if ws else 0
+
+    def release_workspaces(self) -> None:
+        self._workspaces.clear()
+
+    def workspace_bytes(self, height: int, width: int) -> int:
+        ws = self._workspaces.get((height, width))
+        return ws.nbytes if ws else 0
+
+    def _stage_of(self, idx: int) -> tuple[int, str]:
+        for s, st in enumerate(self.stages):
+            if idx == st.conv_idx:
+                return s, "pre"
+            if idx == st.relu_idx:
+                return s, "post"
+            if idx == st.pool_idx:
+                return s, "pool"
+        msg = f"layer index {idx} is not part of the truncated network"
+        raise KeyError(msg)
+
+    def _tap_tensor(self, ws: _Workspace, idx: int) -> torch.Tensor:
+        s, kind = self._stage_of(idx)
+        t = getattr(ws, kind)[s]
+        assert t is not None
+        return t
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _check_image(x: torch.Tensor) -> tuple[int, int]:
+        if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != 3:
+            msg = (f"expected an image tensor of shape [1, 3, H, W], got {tuple(x.shape)} "
+                   "(independent images are independent jobs; the reference folds batch into "
+                   "the Gram channels)")
+            raise ValueError(msg)
+        if x.dtype != torch.float32 or not x.is_cuda:
+            msg = f"expected a float32 CUDA tensor, got {x.dtype} on {x.device}"
+            raise ValueError(msg)
+        return int(x.shape[2]), int(x.shape[3])
+
+    def _run_stack(self, x: torch.Tensor, ws: _Workspace) -> None:
+        cur: torch.Tensor | None = None
+        for s, st in enumerate(self.stages):
+            if s == 0:
+                ops.conv3x3_first_fwd(x, st.weight, st.bias, ws.pre[0], ws.post[0])
+            else:
+                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s])
+            cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
+            if st.pool_idx is not None:
+                ops.maxpool2_fwd(ws.post[s], ws.pool[s])
+                cur = ws.pool[s]
+
+    def compute_targets(self, style_img: torch.Tensor, content_img: torch.Tensor) -> None:
+        """reference core_model.py:192-232 -- Grams of the style image, features of the content
+        image, produced by the same kernels as the per-step forward."""
+        sh, sw = self._check_image(style_img)
+        ch, cw = self._check_image(content_img)
+        ws = self._workspace(sh, sw, with_grad=False)
+        self._run_stack(style_img.contiguous(), ws)
+        grams = []
+        for k, idx in enumerate(self.style_idx):
+            t = self._tap_tensor(ws, idx)
+            g = torch.empty(t.shape[-1], t.shape[-1], device=self.device, dtype=torch.float32)
+            ops.gram_loss_fwd(t, ws.gram_ws[k], gram_out=g)
+            grams.append(g)
+        if (sh, sw) != (ch, cw):
+            del self._workspaces[(sh, sw)]  # style-sized buffers are never needed again
+        ws = self._workspace(ch, cw, with_grad=False)
+        self._run_stack(content_img.contiguous(), ws)
+        feats = [self._tap_tensor(ws, idx).clone() for idx in self.content_idx]
+        self.style_targets = grams
+        self.content_targets_nhwc = feats
+
+    def forward_losses(self, x: torch.Tensor) -> tuple[torch.Tensor, int]:
+        """Run the stack and all losses; returns (view of the loss buffer, workspace generation).
+        Loss order: style layers ascending, then content layers ascending."""
+        if self.style_targets is None or self.content_targets_nhwc is None:
+            msg = "targets must be set before computing losses."
+            raise RuntimeError(msg)
+        h, w = self._check_image(x)
+        ws = self._workspace(h, w, with_grad=False)
+        self._run_stack(x if x.is_contiguous() else x.contiguous(), ws)
+        for k, idx in enumerate(self.style_idx):
+            t = self._tap_tensor(ws, idx)
+            ops.gram_loss_fwd(t, ws.gram_ws[k], target=self.style_targets[k], s_out=ws.s_mat[k],
+                              loss_out=ws.losses[k:k + 1])
+        ns = len(self.style_idx)
+        for k, idx in enumerate(self.content_idx):
+            t = self._tap_tensor(ws, idx)
+            tgt = self.content_targets_nhwc[k]
+            if tgt.shape != t.shape:
+                msg = (f"content target shape {tuple(tgt.shape)} does not match features "
+                       f"{tuple(t.shape)} at layer {idx}")
+                raise RuntimeError(msg)
+            ops.content_loss_fwd(t, tgt, ws.scratch, ws.losses[ns + k:ns + k + 1])
+        ws.generation += 1
+        return ws.losses, ws.generation
+
+    # ------------------------------------------------------------------ backward
+    def _tap_grads(self, ws: _Workspace, idx: int | None, tensor: torch.Tensor | None,
+                   out: torch.Tensor, grad_w: torch.Tensor, accumulate: bool) -> bool:
+        """Accumulate d(loss)/d(tensor) of every loss tapping layer ``idx`` into ``out``."""
+        if idx is None or idx not in self._tapped:
+            return accumulate
+        assert tensor is not None
+        ns = len(self.style_idx)
+        if idx in self.style_idx:
+            k = self.style_idx.index(idx)
+            ops.style_bwd(tensor, ws.s_mat[k], grad_w[k:k + 1], out, accumulate=accumulate)
+            accumulate = True
+        if idx in self.content_idx:
+            k = self.content_idx.index(idx)
+            ops.content_loss_bwd(tensor, self.content_targets_nhwc[k], grad_w[ns + k:ns + k + 1],
+                                 out, accumulate=accumulate)
+            accumulate = True
+        return accumulate
+
+    def backward_losses(self, height: int, width: int, grad_w: torch.Tensor,
+                        generation: int | None = None) -> torch.Tensor:
+        """Input gradient  sum_k grad_w[k] * d(loss_k)/dx  using the activations of the most
+        recent ``forward_losses`` at this image size.  Returns the workspace's NCHW buffer."""
+        ws = self._workspace(height, width, with_grad=True)
+        if generation is not None and generation != ws.generation:
+            msg = ("backward called with stale activations: another forward pass ran on this "
+                   "model (same image size) since the forward being differentiated")
+            raise RuntimeError(msg)
+        grad_w = grad_w.to(torch.float32).contiguous()
+        n = len(self.stages)
+        for s in range(n - 1, -1, -1):
+            st = self.stages[s]
+            down = self.stages[s + 1] if s + 1 < n else None
+            d_y = ws.d_y[s]
+            tap_post = st.relu_idx is not None and st.relu_idx in self._tapped
+            if st.pool_idx is not None:
+                d_pool = ws.d_pool[s]
+                acc = self._tap_grads(ws, st.pool_idx, ws.pool[s], d_pool, grad_w, False)
+                if down is not None:
+                    ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_pool, accumulate=acc)
+                if tap_post:
+                    d_post = ws.d_post[s]
+                    ops.maxpool2_bwd(d_pool, ws.post[s], d_post, relu_mask=False)
+                    self._tap_grads(ws, st.relu_idx, ws.post[s], d_post, grad_w, True)
+                    acc2 = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
+                    ops.relu_bwd(d_post, ws.post[s], d_y, accumulate=acc2)
+                else:
+                    ops.maxpool2_bwd(d_pool, ws.post[s], d_y, relu_mask=True)
+                    self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, True)
+            elif st.relu_idx is not None:
+                if tap_post:
+                    d_post = ws.d_post[s]
+                    acc = self._tap_grads(ws, st.relu_idx, ws.post[s], d_post, grad_w, False)
+                    if down is not None:
+                        ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_post, accumulate=acc)
+                    acc2 = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
+                    ops.relu_bwd(d_post, ws.post[s], d_y, accumulate=acc2)
+                else:
+                    acc = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
+                    # ReLU backward mask fused into the dgrad epilogue
+                    ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_src=ws.post[s],
+                                      accumulate=acc)
+            else:
+                self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
+        ops.conv3x3_first_dgrad(ws.d_y[0], self.stages[0].weight, ws.grad_img)
+        return ws.grad_img
+
+    # ------------------------------------------------------------------ introspection
+    def tap_features_nchw(self, x: torch.Tensor) -> list[torch.Tensor]:
+        """Tapped activations (ascending layer index) as NCHW copies -- for tests."""
+        h, w = self._check_image(x)
+        ws = self._workspace(h, w, with_grad=False)
+        self._run_stack(x.contiguous(), ws)
+        ws.generation += 1
+        return [ops.nhwc_to_nchw(self._tap_tensor(ws, idx)) for idx in sorted(self._tapped)]
+
+    def flops_per_step(self, height: int, width: int) -> dict[str, float]:
+        """Algorithmic FLOPs of one forward + backward at this size."""
+        sizes = self._out_hw(height, width)
+        conv = sum(2.0 * 9 * st.cin * st.cout * h * w for st, (h, w) in zip(self.stages, sizes))
+        gram_tri = 0.0
+        gram_full = 0.0
+        for idx in self.style_idx:
+            s, kind = self._stage_of(idx)
+            h, w = sizes[s]
+            if kind == "pool":
+                h, w = h // 2, w // 2
+            c = self.stages[s].cout
+            gram_full += 2.0 * c * c * h * w
+            gram_tri += 1.0 * c * (c + 1) * h * w
+        return {"conv_fwd": conv, "conv_dgrad": conv, "gram_fwd_full": gram_full,
+                "gram_fwd_tri": gram_tri, "style_bwd": gram_full,
+                "total_tri": 2 * conv + gram_tri + gram_full}

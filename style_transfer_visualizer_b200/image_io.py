@@ -1,0 +1,96 @@
+"""Output-side image helpers of the hot path: de-normalisation and the timelapse frame readback.
+
+``denormalize`` / ``prepare_image_for_output`` keep the reference's semantics (image_io.py:118-152).
+``FrameReadback`` replaces the reference's synchronous ``.cpu().numpy() * 255 -> astype(uint8)``
+(optimization.py:438-452) with ONE fused kernel (denormalise, nan_to_num, clamp, x255, truncate,
+NCHW->HWC) writing 3 bytes per pixel, followed by a pinned-memory D2H copy on a side stream, so
+the compute stream never waits for the copy.  The bytes are identical to the reference's.
+"""
+from __future__ import annotations
+
+from collections import deque
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+from .constants import DENORM_VIEW_SHAPE, IMAGENET_MEAN, IMAGENET_STD
+
+
+def denormalize(tensor: torch.Tensor) -> torch.Tensor:
+    """Undo the ImageNet normalisation (reference image_io.py:118-126)."""
+    mean = torch.tensor(IMAGENET_MEAN).view(*DENORM_VIEW_SHAPE).to(tensor.device)
+    std = torch.tensor(IMAGENET_STD).view(*DENORM_VIEW_SHAPE).to(tensor.device)
+    return tensor * std + mean
+
+
+def prepare_image_for_output(tensor: torch.Tensor, *, normalize: bool) -> torch.Tensor:
+    """Float image in [0, 1] ready for saving (reference image_io.py:129-152)."""
+    img = denormalize(tensor) if normalize else tensor
+    img = torch.nan_to_num(img, nan=0.0, posinf=1.0, neginf=0.0)
+    return img.clamp(0, 1)
+
+
+@dataclass
+class _Ticket:
+    slot: int
+    done: torch.cuda.Event
+    tag: object
+
+
+class FrameReadback:
+    """Ring of (device u8 frame, pinned host frame) pairs + a copy stream."""
+
+    def __init__(self, device: torch.device, height: int, width: int, depth: int = 3) -> None:
+        self.device = device
+        self.shape = (height, width, 3)
+        self.depth = depth
+        self._dev = [torch.empty(self.shape, device=device, dtype=torch.uint8)
+                     for _ in range(depth)]
+        self._host = [torch.empty(self.shape, dtype=torch.uint8).pin_memory()
+                      for _ in range(depth)]
+        self._stream = torch.cuda.Stream(device=device)
+        self._next = 0
+        self._inflight: deque[_Ticket] = deque()
+        self.bytes_per_frame = height * width * 3
+
+    @property
+    def pending(self) -> int:
+        return len(self._inflight)
+
+    def submit(self, img: torch.Tensor, *, normalize: bool, tag: object = None,
+               rounding: bool = False) -> None:
+        """Enqueue conversion (current stream) + D2H (copy stream) of ``img`` [1,3,H,W]."""
+        if len(self._inflight) >= self.depth:
+            msg = "FrameReadback ring is full: collect() before submitting more frames"
+            raise RuntimeError(msg)
+        slot = self._next
+        self._next = (slot + 1) % self.depth
+        src = img.detach()
+        ops.frame_to_u8(src if src.is_contiguous() else src.contiguous(), self._dev[slot],
+                        denormalize=normalize, rounding=rounding)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            self._host[slot].copy_(self._dev[slot], non_blocking=True)
+            done.record(self._stream)
+        self._inflight.append(_Ticket(slot=slot, done=done, tag=tag))
+
+    def collect(self) -> tuple[np.ndarray, object]:
+        """Oldest submitted frame as an owned ``[H, W, 3]`` uint8 array (+ its tag)."""
+        ticket = self._inflight.popleft()
+        ticket.done.synchronize()
+        return self._host[ticket.slot].numpy().copy(), ticket.tag
+
+
+def frame_to_numpy(img: torch.Tensor, *, normalize: bool, rounding: bool = False) -> np.ndarray:
+    """One-shot synchronous variant (fused kernel + blocking copy)."""
+    h, w = int(img.shape[-2]), int(img.shape[-1])
+    out = torch.empty(h, w, 3, device=img.device, dtype=torch.uint8)
+    src = img.detach()
+    ops.frame_to_u8(src if src.is_contiguous() else src.contiguous(), out, denormalize=normalize,
+                    rounding=rounding)
+    return out.cpu().numpy()

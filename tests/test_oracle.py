@@ -1,0 +1,102 @@
+"""Pin the CPU oracle (oracle/stv_oracle.py) against outputs of the real reference.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py running the UNMODIFIED
+reference (core_model.prepare_model_and_input + optimization.OptimizationRunner.run) in the build
+container.  Tolerances are loose enough for a different host CPU (oneDNN kernel selection differs
+between machines) and tight enough to catch any algorithmic divergence.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_shim
+from oracle import stv_oracle as orc
+from tests import _cases as cases
+
+FAST = [n for n in cases.golden_names() if "256" not in n]
+
+
+def _run_oracle(cfg: dict):  # noqa: ANN202
+    content, style, init = cases.case_inputs(cfg)
+    feats = orc.vgg19_features(cfg["weight_seed"])
+    model = orc.OracleModel(feats, cfg["style_layers"], cfg["content_layers"])
+    model.set_targets(style, content)
+    x = cases.initial_image(cfg, content, init).requires_grad_(True)
+    opt = orc.make_optimizer(cfg["opt"], x, cfg["lr"])
+    res = orc.run(model, x, opt, cfg["steps"], style_w=cfg.get("style_w", 1e5),
+                  content_w=cfg.get("content_w", 1.0), save_every=cfg.get("save_every") or 0,
+                  normalize=cfg.get("normalize", True))
+    return model, res
+
+
+def _check(cfg: dict, gold: dict, res: orc.RunResult, *, rtol: float) -> None:
+    np.testing.assert_allclose(res.layer_style, gold["layer_style"], rtol=rtol, atol=1e-30)
+    np.testing.assert_allclose(res.layer_content, gold["layer_content"], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(res.total, gold["total_loss"], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(res.style, gold["style_loss"], rtol=rtol, atol=1e-30)
+    grad = cases.subsample_like_golden(cfg, res.first_grad)
+    assert cases.rel_l2(grad, gold["first_grad"]) < rtol
+    final = cases.subsample_like_golden(cfg, res.final)
+    assert cases.rel_l2(final, gold["final"]) < rtol
+    if "frames" in gold and gold["frames"].size:
+        frames = np.stack(res.frames)
+        if cfg["h"] * cfg["w"] > 128 * 128:
+            frames = frames[:, ::4, ::4, :]
+        diff = np.abs(frames.astype(int) - gold["frames"].astype(int))
+        assert diff.max() <= 1  # a 1-LSB flip is possible when a value sits on a truncation edge
+        assert (diff > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_oracle_matches_reference_golden(name: str) -> None:
+    cfg, gold = cases.load_golden(name)
+    _model, res = _run_oracle(cfg)
+    _check(cfg, gold, res, rtol=2e-3 if cfg["opt"] == "lbfgs" else 5e-4)
+
+
+@pytest.mark.slow
+def test_oracle_matches_reference_golden_c1_256() -> None:
+    """BASELINE.json configs[0]: 256x256, Adam, 50 steps, content init, CPU."""
+    cfg, gold = cases.load_golden("adam_content_256_c1")
+    _model, res = _run_oracle(cfg)
+    _check(cfg, gold, res, rtol=2e-3)
+    assert res.content[0] == 0.0  # content init => exactly zero content loss at step 1
+
+
+def test_gram_properties() -> None:
+    """The structural pins the reference's own tests hold (tests/test_core_model.py:84-92)."""
+    t = torch.randn(1, 16, 9, 11)
+    g = orc.gram_matrix(t)
+    assert g.shape == (16, 16)
+    assert torch.allclose(g, g.t(), atol=1e-6)
+    assert torch.linalg.eigvalsh(g.double()).min() >= -1e-6
+    big = orc.gram_matrix(t * 1e4)
+    assert float(big.max()) <= orc.GRAM_MATRIX_CLAMP_MAX / t[0].numel() * (1 + 1e-6)
+
+
+@pytest.mark.skipif(not reference_shim.available(), reason="reference tree not mounted")
+def test_oracle_matches_live_reference() -> None:
+    """Same inputs through the real reference modules and the restatement: identical numbers."""
+    ref = reference_shim.load()
+    reference_shim.patch_random_vgg(ref, 0)
+    content = orc.synthetic_image(1, 64, 80)
+    style = orc.synthetic_image(2, 72, 64)
+    cfg = ref.config.OptimizationConfig.model_validate({"init_method": "content"})
+    model, _img, _opt = ref.core_model.prepare_model_and_input(content, style,
+                                                               torch.device("cpu"), cfg)
+    mine = orc.OracleModel(orc.vgg19_features(0))
+    mine.set_targets(style, content)
+    x = torch.randn(1, 3, 64, 80, generator=torch.Generator().manual_seed(5))
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    sl_a, cl_a = model(xa)
+    sl_b, cl_b = mine(xb)
+    (1e5 * torch.stack(sl_a).sum() + torch.stack(cl_a).sum()).backward()
+    (1e5 * torch.stack(sl_b).sum() + torch.stack(cl_b).sum()).backward()
+    assert [float(v) for v in sl_a] == [float(v) for v in sl_b]
+    assert [float(v) for v in cl_a] == [float(v) for v in cl_b]
+    assert torch.equal(xa.grad, xb.grad)
+    assert torch.equal(ref.core_model.gram_matrix(x.repeat(1, 2, 1, 1)[:, :4]),
+                       orc.gram_matrix(x.repeat(1, 2, 1, 1)[:, :4]))
