@@ -1,0 +1,391 @@
+"""Benchmark of the optimisation hot path (BASELINE.json metric: optimisation steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 512|1080p] [--impl reference]
+
+One "step" = one full optimisation step of the reference's runner (VGG19 forward, Gram/MSE losses,
+dgrad backward, Adam update of the image).  At N=1 the workload is BASELINE.json configs[1]
+(VGG19 512x512, default style/content layers, Adam, random-init weights, synthetic images); with
+N>1 (torchrun, one rank per GPU) every rank runs its own independent content/style pair
+(configs[3]: independent jobs, no data-path collective => weak scaling).  Rank 0 prints ONE JSON
+line.  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "512": dict(h=512, w=512, save_every=0, steps=300,
+                name="configs[1]: VGG19 512x512, Adam, default style/content layers, "
+                     "content init, random-init weights, synthetic images"),
+    "1080p": dict(h=1080, w=1920, save_every=10, steps=100,
+                  name="configs[2]: VGG19 1920x1080, Adam, save_every=10 frame readback, "
+                       "content init, random-init weights, synthetic images"),
+}
+METRIC = "optimization steps/sec"
+STYLE_W, CONTENT_W, LR = 1e5, 1.0, 0.01
+
+
+def _peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(h: int, w: int, *, budget_s: float, max_steps: int, min_steps: int = 2):
+    """Time the reference's algorithm (oracle port: same torch ops at the reference's call sites)
+    on all host threads.  Returns (steps/sec, steps timed, threads)."""
+    import torch
+
+    from oracle import stv_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    content = orc.synthetic_image(1, h, w)
+    style = orc.synthetic_image(2, h, w)
+    model = orc.OracleModel(orc.vgg19_features(0))
+    model.set_targets(style, content)
+    x = orc.initialize_input(content, "content")
+    opt = orc.make_optimizer("adam", x, LR)
+
+    def closure():
+        return orc.closure_step(model, x, STYLE_W, CONTENT_W)[2]
+
+    opt.step(closure)  # warm-up (thread pools, oneDNN primitive caches)
+    done, t0 = 0, time.perf_counter()
+    while done < max_steps:
+        opt.step(closure)
+        done += 1
+        if done >= min_steps and time.perf_counter() - t0 > budget_s:
+            break
+    elapsed = time.perf_counter() - t0
+    return done / elapsed, done, torch.get_num_threads()
+
+
+def run_reference_arm(args, wl) -> None:  # noqa: ANN001
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, done, threads = cpu_reference_run(wl["h"], wl["w"], budget_s=90.0,
+                                             max_steps=max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": 1, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "height": wl["h"], "width": wl["w"],
+                   "optimizer": "adam", "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{done} of {args.steps} requested steps at full resolution "
+                                   "(90 s time budget), oracle port of the reference's path"},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)  # noqa: SIM115
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in Path(self.path).read_text().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        Path(self.path).unlink(missing_ok=True)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_job(device, h: int, w: int, seed_offset: int):  # noqa: ANN001
+    """Model (random-init VGG19, seed 0) + pinned host images for one content/style pair."""
+    import torch
+
+    import style_transfer_visualizer_b200.core_model as cm
+    from oracle import stv_oracle as orc  # input/weight generators shared with the CPU arm
+
+    original = cm.initialize_vgg
+    cm.initialize_vgg = lambda: orc.vgg19_features(0)
+    try:
+        model = cm.StyleContentModel(list(orc.DEFAULT_STYLE_LAYERS),
+                                     list(orc.DEFAULT_CONTENT_LAYERS)).to(device)
+    finally:
+        cm.initialize_vgg = original
+    content = orc.synthetic_image(1 + 2 * seed_offset, h, w).pin_memory()
+    style = orc.synthetic_image(2 + 2 * seed_offset, h, w).pin_memory()
+    torch.cuda.synchronize(device)
+    return model, content, style
+
+
+def profile_dominant_kernel(model, x, steps: int) -> dict:  # noqa: ANN001
+    """CUDA-event timing of every tensor-core conv launch (fwd, dgrad, style-bwd 1x1) over `steps`
+    eager executions of the step; returns algorithmic FLOPs, total time and launch count."""
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    records: list[tuple[float, torch.cuda.Event, torch.cuda.Event]] = []
+    orig = (ops.conv3x3_fwd, ops.conv3x3_dgrad, ops.style_bwd)
+
+    def timed(fn, flops_of):  # noqa: ANN001, ANN202
+        def wrapper(*a, **k):  # noqa: ANN002, ANN003, ANN202
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a, **k)
+            e1.record()
+            records.append((flops_of(*a, **k), e0, e1))
+        return wrapper
+
+    ops.conv3x3_fwd = timed(orig[0], lambda x_, wf, *a, **k: 2.0 * 9 * x_.numel() * wf.shape[1])
+    ops.conv3x3_dgrad = timed(orig[1], lambda dy, wd, *a, **k: 2.0 * 9 * dy.numel() * wd.shape[1])
+    ops.style_bwd = timed(orig[2], lambda x_, s, *a, **k: 2.0 * x_.numel() * s.shape[0])
+    try:
+        for _ in range(steps):
+            xx = x.detach().clone().requires_grad_(True)
+            sl, cl = model(xx)
+            (STYLE_W * torch.stack(sl).sum() + CONTENT_W * torch.stack(cl).sum()).backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3x3_fwd, ops.conv3x3_dgrad, ops.style_bwd = orig
+    flops = sum(r[0] for r in records)
+    ms = sum(r[1].elapsed_time(r[2]) for r in records)
+    return {"flops": flops, "ms": ms, "launches": len(records), "steps": steps}
+
+
+def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
+    import torch
+
+    from style_transfer_visualizer_b200 import _native as nat
+    from style_transfer_visualizer_b200 import jobs
+    from style_transfer_visualizer_b200.config import StyleTransferConfig
+    from style_transfer_visualizer_b200.optim import FusedAdam
+    from style_transfer_visualizer_b200.optimization import OptimizationRunner
+
+    info = jobs.init_distributed()
+    device = torch.device("cuda", info.local_rank)
+    torch.cuda.set_device(device)
+    nat.require_device(device)  # fails loudly if the .so is missing or the GPU is not sm_100
+    h, w, k_steps, warm = wl["h"], wl["w"], args.steps, max(3, args.warmup)
+
+    class Bar:
+        def update(self, n=1): ...  # noqa: ANN001, ANN201
+        def set_postfix(self, *a, **k): ...  # noqa: ANN002, ANN003, ANN201
+        def close(self): ...  # noqa: ANN201
+
+    class Sink:
+        _size = None
+        count = 0
+
+        def append_data(self, f):  # noqa: ANN001, ANN201
+            Sink.count += 1
+
+        def close(self): ...  # noqa: ANN201
+
+    def make_cfg(steps: int, log_every: int):  # noqa: ANN202
+        return StyleTransferConfig.model_validate({
+            "optimization": {"steps": steps, "style_w": STYLE_W, "content_w": CONTENT_W, "lr": LR,
+                             "init_method": "content", "optimizer": "adam"},
+            "video": {"save_every": wl["save_every"] or steps + 1},
+            "output": {"log_every": log_every}})
+
+    model, content_h, style_h = build_job(device, h, w, info.rank)
+
+    # ---- device-resident measurement: inputs already in HBM when the timed region starts -------
+    from style_transfer_visualizer_b200.core_model import initialize_input
+
+    content = content_h.to(device, non_blocking=True)
+    style = style_h.to(device, non_blocking=True)
+    model.set_targets(style, content)
+    x = initialize_input(content, "content")
+    opt = FusedAdam([x], lr=LR)
+    sink = Sink() if wl["save_every"] else None
+    runner = OptimizationRunner(model, x, make_cfg(warm + k_steps, 10), optimizer=opt,
+                                progress_bar=Bar(), video_writer=sink, use_cuda_graph=True)
+    runner._ensure_progress_bar()  # noqa: SLF001
+    runner._maybe_build_fused_step()  # noqa: SLF001
+
+    def one_step() -> None:
+        idx = runner._step_index + 1  # noqa: SLF001
+        runner._active_step_idx = idx  # noqa: SLF001
+        runner._fused_step(idx)  # noqa: SLF001
+        runner._finalize_step(runner._pending_step_tensors)  # noqa: SLF001
+
+    launches_before = nat.launch_count()
+    for _ in range(warm):
+        one_step()
+    launches_per_step = runner._fused.kernel_launches  # noqa: SLF001
+    torch.cuda.synchronize(device)
+    jobs.barrier()
+    sampler = ClockSampler(info.local_rank) if info.rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(k_steps):
+        one_step()
+    runner._drain_frames()  # noqa: SLF001
+    e1.record()
+    torch.cuda.synchronize(device)
+    jobs.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_local = e0.elapsed_time(e1)
+    ms_total = jobs.max_over_ranks(ms_local, device)
+    value = info.world_size * k_steps / (ms_total / 1e3)
+    del launches_before
+
+    # ---- end to end through the public API: pinned host inputs, H2D + per-step loss D2H -------
+    e2e_steps = min(k_steps, 100)
+    torch.cuda.synchronize(device)
+    jobs.barrier()
+    t0 = time.perf_counter()
+    c_dev = content_h.to(device, non_blocking=True)
+    s_dev = style_h.to(device, non_blocking=True)
+    model.set_targets(s_dev, c_dev)
+    x2 = initialize_input(c_dev, "content")
+    runner2 = OptimizationRunner(model, x2, make_cfg(e2e_steps, 1),
+                                 optimizer=FusedAdam([x2], lr=LR), progress_bar=Bar(),
+                                 video_writer=Sink() if wl["save_every"] else None)
+    final, hist, _ = runner2.run()
+    final_host = final.detach().cpu()
+    torch.cuda.synchronize(device)
+    e2e_s = jobs.max_over_ranks(time.perf_counter() - t0, device)
+    assert len(hist["total_loss"]) == e2e_steps
+    h2d = (content_h.numel() + style_h.numel()) * 4 / e2e_steps
+    d2h = 12 + final_host.numel() * 4 / e2e_steps + runner2.frame_bytes_d2h / e2e_steps
+    e2e_value = info.world_size * e2e_steps / e2e_s
+
+    if info.rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (tensor-core conv), measured live with CUDA events ----
+    prof = profile_dominant_kernel(model, x, 3)
+    peaks = _peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    achieved = prof["flops"] / (prof["ms"] / 1e3) / 1e12
+    traffic = None
+    rf = ROOT / "profiles" / "roofline_traffic.json"
+    if rf.exists():
+        traffic = json.loads(rf.read_text()).get(args.workload)
+    step_flops = model.engine_for(device).flops_per_step(h, w)
+    roofline = {
+        "bound": "tensor", "kernel": "conv_igemm_tf32_kernel (3x3 fwd + dgrad, 1x1 style-bwd)",
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "traffic": traffic,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (TF32 tensor rate is half "
+                       "the bf16 rate)",
+        "launches_per_step": prof["launches"] // prof["steps"],
+        "avg_launch_ms": prof["ms"] / prof["launches"],
+        "algorithmic_flops_per_step": prof["flops"] / prof["steps"],
+        "share_of_step_time": (prof["ms"] / prof["steps"]) / (ms_total / k_steps),
+        "whole_step_tflops": step_flops["total_tri"] / (ms_total / k_steps / 1e3) / 1e12,
+        "measured_on": "3 eager executions of the same step, one CUDA-event pair per launch",
+    }
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------
+    cpu = None
+    if info.world_size == 1 and not args.no_cpu_baseline:
+        v, done, threads = cpu_reference_run(h, w, budget_s=12.0, max_steps=20)
+        cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"{done} Adam steps at {w}x{h} (12 s budget) of the oracle port of the "
+                         "reference's path, all host threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": info.world_size,
+        "steps": k_steps, "warmup": warm, "ms_per_step": ms_total / k_steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "height": h, "width": w, "optimizer": "adam",
+                   "lr": LR, "style_w": STYLE_W, "content_w": CONTENT_W,
+                   "jobs_per_gpu": 1, "parallelism": f"independent jobs x{info.world_size}",
+                   "l2": "no flush: each step streams ~%.1f GB of activations/gradients, far above "
+                         "the 126 MB L2" % (model.engine_for(device).workspace_bytes(h, w) / 1e9),
+                   "storage": "fp32 activations, TF32 multiply / FP32 accumulate"},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "how": "pinned host images -> H2D -> set_targets -> OptimizationRunner.run() with "
+                       "log_every=1 (loss D2H every step) -> final image D2H"},
+        "gpu_launches": launches_per_step * k_steps,
+        "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "frames_read_back": Sink.count,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="512", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = wl["steps"]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_gpu_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

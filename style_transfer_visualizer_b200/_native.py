@@ -103,9 +103,22 @@ def stream_ptr(device: torch.device | None = None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+# kernels enqueued per entry point (everything else launches exactly one)
+_KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_content_loss_fwd": 2, "stv_dot": 2,
+                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_abi_version": 0,
+                     "stv_device_check": 0}
+_launches = [0]
+
+
+def launch_count() -> int:
+    """Kernels of this library enqueued so far by this process (graph replays not included)."""
+    return _launches[0]
+
+
 def call(name: str, *args) -> None:  # noqa: ANN002
     """Invoke an int-status entry point; raise with the library's message on failure."""
     lib = load()
+    _launches[0] += _KERNELS_PER_CALL.get(name, 1)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         detail = lib.stv_last_error().decode("utf-8", "replace")

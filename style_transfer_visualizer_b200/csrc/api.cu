@@ -114,14 +114,15 @@ int stv_conv3x3_first_fwd(const float* img_nchw, const float* w, const float* bi
 
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
                     int Cout, float* out_pre, float* out_post, void* stream) {
+  // out_post feeds the next conv's MMA -> stored tf32-rounded; out_pre (read by the losses) exact.
   return conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
-                           out_post, 0, 0, 0, S(stream));
+                           out_post, 2, 0, 0, 0, S(stream));
 }
 
 int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                       const float* relu_src, int accumulate, float* dx, void* stream) {
   return conv_igemm_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
-                           accumulate ? dx : nullptr, dx, nullptr, 0, 0, 0, S(stream));
+                           accumulate ? dx : nullptr, dx, nullptr, 1, 0, 0, 0, S(stream));
 }
 
 int stv_conv3x3_first_dgrad(const float* dy, const float* w, int H, int W, int Cout,
@@ -159,7 +160,7 @@ int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* g
   // (symmetric, so its rows serve directly as the K-major B operand).
   STV_REQUIRE(hw <= 0x7fffffffL, "style_bwd: feature map too large");
   return conv_igemm_launch(x, s, 1, static_cast<int>(hw), C, C, 1, nullptr, grad_w, nullptr,
-                           accumulate ? dy : nullptr, dy, nullptr, 0, 1, 128, S(stream));
+                           accumulate ? dy : nullptr, dy, nullptr, 1, 0, 1, 128, S(stream));
 }
 
 int stv_reduce_scratch_floats(void) { return reduce_scratch_floats(); }
@@ -214,7 +215,7 @@ int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C
                       const float* add_src, float* out_pre, float* out_post, int block_n, int th,
                       int tw, void* stream) {
   return conv_igemm_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
-                           out_post, block_n, th, tw, S(stream));
+                           out_post, 0, block_n, th, tw, S(stream));
 }
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream) {

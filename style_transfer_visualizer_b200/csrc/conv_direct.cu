@@ -65,8 +65,9 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
     if (pre) reinterpret_cast<float4*>(pre)[c4] = acc;
     if (post) {
       float4 o;
-      o.x = fmaxf(acc.x, 0.f); o.y = fmaxf(acc.y, 0.f);
-      o.z = fmaxf(acc.z, 0.f); o.w = fmaxf(acc.w, 0.f);
+      // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
+      o.x = round_tf32(fmaxf(acc.x, 0.f)); o.y = round_tf32(fmaxf(acc.y, 0.f));
+      o.z = round_tf32(fmaxf(acc.z, 0.f)); o.w = round_tf32(fmaxf(acc.w, 0.f));
       reinterpret_cast<float4*>(post)[c4] = o;
     }
   }

@@ -37,6 +37,8 @@ struct ConvIgemmParams {
   const float* add_src;   // NHWC [H,W,N]: added after masking (gradient accumulation)
   float* out_pre;         // result before ReLU (or the only result); may be null
   float* out_post;        // max(result, 0); may be null
+  int round_pre;          // store out_pre rounded to tf32 (it feeds another MMA as an operand)
+  int round_post;         // store out_post rounded to tf32
 };
 
 constexpr int kThreads = 192;
@@ -186,11 +188,22 @@ conv_igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             const float4 a = *reinterpret_cast<const float4*>(p.add_src + row_off + col);
             v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
           }
-          if (p.out_pre) *reinterpret_cast<float4*>(p.out_pre + row_off + col) = v;
+          if (p.out_pre) {
+            float4 o = v;
+            if (p.round_pre) {
+              o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+              o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            }
+            *reinterpret_cast<float4*>(p.out_pre + row_off + col) = o;
+          }
           if (p.out_post) {
             float4 o;
             o.x = fmaxf(v.x, 0.f); o.y = fmaxf(v.y, 0.f);
             o.z = fmaxf(v.z, 0.f); o.w = fmaxf(v.w, 0.f);
+            if (p.round_post) {
+              o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+              o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            }
             *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
           }
         }
@@ -243,8 +256,8 @@ static void pick_patch(int H, int W, int* th, int* tw) {
 
 int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
                       const float* bias, const float* alpha, const float* mask_src,
-                      const float* add_src, float* out_pre, float* out_post, int block_n,
-                      int th, int tw, cudaStream_t stream) {
+                      const float* add_src, float* out_pre, float* out_post, int round_flags,
+                      int block_n, int th, int tw, cudaStream_t stream) {
   STV_REQUIRE(C % 32 == 0 && C >= 32, "conv_igemm: input channels %d must be a multiple of 32", C);
   STV_REQUIRE(N % 64 == 0, "conv_igemm: output channels %d must be a multiple of 64", N);
   STV_REQUIRE(taps == 9 || taps == 1, "conv_igemm: taps must be 9 or 1 (got %d)", taps);
@@ -283,6 +296,7 @@ int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C
   p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.th = th; p.tw = tw; p.tiles_x = tiles_x;
   p.bias = bias; p.alpha = alpha; p.mask_src = mask_src; p.add_src = add_src;
   p.out_pre = out_pre; p.out_post = out_post;
+  p.round_pre = round_flags & 1; p.round_post = (round_flags >> 1) & 1;
 
   switch (block_n) {
     case 64:  return launch_conv<64, 4>(tx, twm, p, tiles, stream);

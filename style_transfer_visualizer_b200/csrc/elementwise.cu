@@ -33,7 +33,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, float* __r
     const long r = i / 9;
     const int ci = static_cast<int>(r % Cin);
     const int co = static_cast<int>(r / Cin);
-    const float v = w[i];
+    const float v = round_tf32(w[i]);  // MMA operand: round once here instead of truncating
     if (wf) wf[(static_cast<long>(tap) * Cout + co) * Cin + ci] = v;
     if (wd) wd[(static_cast<long>(8 - tap) * Cin + ci) * Cout + co] = v;
   }
@@ -144,7 +144,8 @@ __global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __r
       const float4 p = dx[i];
       o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
     }
-    dx[i] = o;
+    o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+    dx[i] = o;  // gradient buffers are dgrad MMA operands: keep them tf32-exact
   }
 }
 __global__ void add_inplace_kernel(float4* dst, const float4* __restrict__ src, long n4) {
@@ -220,12 +221,13 @@ content_bwd_kernel(const float* __restrict__ f, const float* __restrict__ t, lon
       const float4 p = d4[i];
       o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
     }
+    o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
     d4[i] = o;
   }
   if (blockIdx.x == 0)
     for (long i = (n4 << 2) + threadIdx.x; i < n; i += 256) {
       const float o = k * (f[i] - t[i]);
-      df[i] = accumulate ? df[i] + o : o;
+      df[i] = round_tf32(accumulate ? df[i] + o : o);
     }
 }
 

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const GramFinalizePa
       const float d = g - p.target[static_cast<size_t>(i) * p.C + j];
       contrib = off_diag ? 2.f * d * d : d * d;
       if (p.s_out) {
-        const float sv = (r <= p.clamp_max) ? d * p.s_scale : 0.f;
+        const float sv = (r <= p.clamp_max) ? round_tf32(d * p.s_scale) : 0.f;  // MMA operand
         p.s_out[static_cast<size_t>(i) * p.C + j] = sv;
         if (off_diag) p.s_out[static_cast<size_t>(j) * p.C + i] = sv;
       }

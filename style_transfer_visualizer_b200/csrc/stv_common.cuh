@@ -250,6 +250,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
          | (uint32_t(M >> 4) << 24);    // M / 16
 }
 
+// Round-to-nearest fp32 -> tf32 (result kept in an fp32 container, low 13 mantissa bits zero).
+// The tensor core TRUNCATES fp32 operands to tf32; rounding in the producer removes the
+// systematic shrink that truncation would compound layer after layer.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,11 +6,12 @@ namespace stv {
 
 // conv_igemm.cu ---------------------------------------------------------------------------
 // out = [relu-mask](alpha * conv(x, w) + bias) + add ; writes out_pre and/or relu(out) to out_post.
+// round_flags: bit 0 = store out_pre rounded to tf32, bit 1 = store out_post rounded to tf32.
 // block_n / th / tw <= 0 select the heuristics.
 int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
                       const float* bias, const float* alpha, const float* mask_src,
-                      const float* add_src, float* out_pre, float* out_post, int block_n, int th,
-                      int tw, cudaStream_t stream);
+                      const float* add_src, float* out_pre, float* out_post, int round_flags,
+                      int block_n, int th, int tw, cudaStream_t stream);
 
 // gram.cu ---------------------------------------------------------------------------------
 size_t gram_workspace_bytes(long hw, int C);

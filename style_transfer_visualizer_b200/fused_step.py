@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _native as nat
 from . import ops
 from .core_model import StyleContentModel
 from .optim import FusedAdam
@@ -93,8 +94,10 @@ class FusedStep:
             torch.cuda.current_stream(self.x.device).wait_stream(side)
             torch.cuda.synchronize(self.x.device)
             graph = torch.cuda.CUDAGraph()
+            before = nat.launch_count()
             with torch.cuda.graph(graph):
                 self._body()
+            self.kernel_launches = nat.launch_count() - before  # this library's kernels per replay
             self.graph = graph
         # like the reference, the image carries the last gradient after each step
         self.x.grad = self.engine.grad_buffer(self.height, self.width)

@@ -1,0 +1,352 @@
+"""CPU tests of the host side: C-ABI symbol coverage, config / CLI, loss logging hooks and the
+runner's behavioural contract (modelled on the reference's tests/test_optimization.py,
+test_loss_accumulator.py, test_loss_logger.py, test_config.py).  No kernel is launched here."""
+from __future__ import annotations
+
+import csv
+import logging
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from style_transfer_visualizer_b200 import _native as nat
+from style_transfer_visualizer_b200.config import (ConfigLoader, StyleTransferConfig,
+                                                   build_config_from_cli, parse_int_list)
+from style_transfer_visualizer_b200.loss_accumulator import LossAccumulator
+from style_transfer_visualizer_b200.loss_logger import LossCSVLogger
+from style_transfer_visualizer_b200.optimization import (OptimizationCallbacks,
+                                                         OptimizationRunner, StepMetrics)
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+# --------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol() -> None:
+    header = (ROOT / "include" / "stv_b200.h").read_text()
+    declared = set(re.findall(r"\b(stv_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    lib = nat.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in stv_b200.h but not exported"
+    assert declared == set(nat.EXPORTED_SYMBOLS)
+    assert lib.stv_abi_version() == 1
+    assert lib.stv_reduce_scratch_floats() > 0
+    assert lib.stv_gram_workspace_bytes(64 * 64, 64) > 0
+
+
+def test_no_cpu_fallback() -> None:
+    """The product path must fail loudly off-GPU (it never routes through the oracle)."""
+    import style_transfer_visualizer_b200.core_model as cm
+    from oracle import stv_oracle as orc
+
+    with pytest.raises(nat.NativeLibraryError, match="no CPU fallback"):
+        nat.require_device(torch.device("cpu"))
+    original = cm.initialize_vgg
+    cm.initialize_vgg = lambda: orc.vgg19_features(0)
+    try:
+        model = cm.StyleContentModel([0, 5], [2])
+    finally:
+        cm.initialize_vgg = original
+    img = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(nat.NativeLibraryError):
+        model.set_targets(img, img)
+    with pytest.raises(RuntimeError, match="style_targets must be set"):
+        model(img)
+    src = "".join(p.read_text() for p in (ROOT / "style_transfer_visualizer_b200").glob("*.py"))
+    assert "oracle" not in src.replace("oracle/", "")  # the package never imports the oracle
+
+
+def test_feature_blocks_match_reference_layout() -> None:
+    """Default taps cut vgg19.features into the 6 blocks of SURVEY section 3.3."""
+    import style_transfer_visualizer_b200.core_model as cm
+    from oracle import stv_oracle as orc
+
+    blocks, content_ids, style_ids = cm.create_feature_blocks(
+        orc.vgg19_features(0), [0, 5, 10, 19, 28], [21])
+    assert [len(b) for b in blocks] == [1, 5, 5, 9, 2, 7]
+    assert style_ids == [0, 1, 2, 3, 5] and content_ids == [4]
+    assert not any(m.inplace for b in blocks for m in b if isinstance(m, nn.ReLU))
+    x = torch.zeros(1, 3, 8, 8)
+    with pytest.raises(ValueError, match="Unsupported initialization method"):
+        cm.initialize_input(x, "bogus")  # type: ignore[arg-type]
+    with pytest.raises(TypeError):
+        cm.initialize_input("x", "content")  # type: ignore[arg-type]
+    assert cm.initialize_input(x, "white").requires_grad
+    assert torch.equal(cm.initialize_input(x + 2, "content").detach(), x + 2)
+
+
+# --------------------------------------------------------------------------- config / CLI
+def test_config_defaults_and_bounds() -> None:
+    cfg = StyleTransferConfig.model_validate({})
+    assert cfg.optimization.steps == 1500 and cfg.optimization.style_w == 1e5
+    assert cfg.optimization.lr == 1.0 and cfg.optimization.init_method == "random"
+    assert cfg.optimization.style_layers == [0, 5, 10, 19, 28]
+    assert cfg.optimization.content_layers == [21]
+    assert cfg.video.save_every == 20 and cfg.output.log_every == 10
+    assert cfg.hardware.device == "cuda"
+    with pytest.raises(ValueError):  # noqa: PT011
+        StyleTransferConfig.model_validate({"optimization": {"steps": 0}})
+    with pytest.raises(ValueError):  # noqa: PT011
+        StyleTransferConfig.model_validate({"video": {"fps": 61}})
+
+
+def test_cli_overrides_and_toml(tmp_path: Path, caplog: pytest.LogCaptureFixture) -> None:
+    toml = tmp_path / "config.toml"
+    toml.write_text("[optimization]\nsteps = 7\nstyle_w = 3.0\n[video]\nsave_every = 4\n"
+                    "[output]\nlog_every = 2\n")
+    base = ConfigLoader.load(str(toml))
+    assert base.optimization.steps == 7 and base.video.save_every == 4
+    cfg = build_config_from_cli({"config": str(toml), "steps": 9, "style_layers": "0,2,4",
+                                 "no_normalize": True, "final_only": True})
+    assert cfg.optimization.steps == 9 and cfg.optimization.style_w == 3.0
+    assert cfg.optimization.style_layers == [0, 2, 4] and not cfg.optimization.normalize
+    assert cfg.video.final_only and cfg.output.log_every == 2
+    assert parse_int_list("1, 2,3") == [1, 2, 3] and parse_int_list([4]) == [4]
+    with pytest.raises(FileNotFoundError):
+        ConfigLoader.load(str(tmp_path / "missing.toml"))
+    from style_transfer_visualizer_b200.logging_utils import logger
+
+    logger.propagate = True
+    try:
+        with caplog.at_level(logging.WARNING, logger="style_transfer"):
+            cfg = build_config_from_cli({"log_loss": str(tmp_path / "l.csv")})
+    finally:
+        logger.propagate = False
+    assert not cfg.output.plot_losses
+    assert "Loss plotting is disabled" in caplog.text
+    from style_transfer_visualizer_b200.cli import build_arg_parser
+
+    ns = build_arg_parser().parse_args(["--content", "c.png", "--style", "s.png", "--steps", "3"])
+    assert vars(ns)["steps"] == 3 and "lr" not in vars(ns)
+
+
+# --------------------------------------------------------------------------- logging hooks
+def test_csv_logger_rows_and_cadence(tmp_path: Path) -> None:
+    path = tmp_path / "sub" / "loss.csv"
+    with LossCSVLogger(path, log_every=2) as lg:
+        for step in range(1, 6):
+            lg.log(step, 1.0, 0.5, 1.5)
+    rows = list(csv.reader(path.open()))
+    assert rows[0] == ["step", "style_loss", "content_loss", "total_loss"]
+    assert rows[1:] == [["2", "1.0", "0.5", "1.5"], ["4", "1.0", "0.5", "1.5"]]
+    lg.close()  # idempotent
+
+
+def test_loss_accumulator_sync_cadence_and_ring() -> None:
+    acc = LossAccumulator(log_every=3, history_capacity=4, track_history=True,
+                          device=torch.device("cpu"), dtype=torch.float32)
+    calls = []
+    acc._to_float = lambda t: calls.append(1) or float(t)  # noqa: SLF001
+    out = [acc.accumulate(i, torch.tensor(float(i)), torch.tensor(2.0 * i), torch.tensor(3.0 * i))
+           for i in range(1, 8)]
+    assert [o is not None for o in out] == [False, False, True, False, False, True, False]
+    assert len(calls) == 6 and out[5].step == 6 and out[5].total_loss == 18.0
+    hist = acc.export_history()
+    assert hist["style_loss"] == [4.0, 5.0, 6.0, 7.0] and acc.history_truncated
+    assert acc.accumulate(8, torch.tensor(1.0), torch.tensor(1.0), torch.tensor(1.0),
+                          force=True).step == 8
+    assert acc.latest().step == 8
+    empty = LossAccumulator(log_every=1, history_capacity=None, track_history=False,
+                            device=torch.device("cpu"), dtype=torch.float32)
+    assert empty.export_history() == {"style_loss": [], "content_loss": [], "total_loss": []}
+    assert empty.capacity == 2048 and not empty.tracks_history
+
+
+# --------------------------------------------------------------------------- runner contract
+class TinyModel(nn.Module):
+    """Duck-typed model: forward(x) -> ([style], [content]) attached to x's graph."""
+
+    def forward(self, x: torch.Tensor):  # noqa: ANN201
+        return [(x ** 2).mean()], [(x - 1).abs().mean()]
+
+
+class Bar:
+    def __init__(self) -> None:
+        self.updates = 0
+        self.postfix = []
+        self.closed = False
+
+    def update(self, n=1):  # noqa: ANN001, ANN201
+        self.updates += n
+
+    def set_postfix(self, d=None, **k):  # noqa: ANN001, ANN003, ANN201
+        self.postfix.append(d)
+
+    def close(self):  # noqa: ANN201
+        self.closed = True
+
+
+class Sink:
+    def __init__(self) -> None:
+        self.frames = []
+        self._size = None
+
+    def append_data(self, f):  # noqa: ANN001, ANN201
+        self.frames.append(f)
+
+    def close(self):  # noqa: ANN201
+        pass
+
+
+class MultiProbeSGD(torch.optim.SGD):
+    """Evaluates the closure several times per step (like a line-search optimiser)."""
+
+    def step(self, closure=None):  # noqa: ANN001, ANN201
+        for _ in range(3):
+            loss = closure()
+        super().step()
+        return loss
+
+
+def _cfg(steps: int = 6, **kw) -> StyleTransferConfig:  # noqa: ANN003
+    return StyleTransferConfig.model_validate({
+        "optimization": {"steps": steps, "normalize": kw.get("normalize", False)},
+        "video": {"save_every": kw.get("save_every", 2)},
+        "output": {"log_every": kw.get("log_every", 2), "log_loss": kw.get("log_loss")},
+    })
+
+
+def _img() -> torch.Tensor:
+    return torch.rand(1, 3, 8, 8).requires_grad_(True)
+
+
+def test_runner_history_frames_progress() -> None:
+    x = _img()
+    sink, bar = Sink(), Bar()
+    seen: list[StepMetrics] = []
+    frames_cb: list[int] = []
+    starts: list[int] = []
+    cbs = OptimizationCallbacks(on_step_start=starts.append, on_step_end=seen.append,
+                                on_video_frame=lambda f, s: frames_cb.append(s))
+    runner = OptimizationRunner(TinyModel(), x, _cfg(), optimizer=torch.optim.Adam([x], lr=0.1),
+                                progress_bar=bar, callbacks=cbs, video_writer=sink)
+    out, hist, elapsed = runner.run()
+    assert out is x and elapsed >= 0
+    assert all(len(hist[k]) == 6 for k in ("style_loss", "content_loss", "total_loss"))
+    assert hist["total_loss"][-1] < hist["total_loss"][0]
+    assert len(sink.frames) == 3 and frames_cb == [2, 4, 6] and starts == [1, 2, 3, 4, 5, 6]
+    assert sink.frames[0].dtype == np.uint8 and sink.frames[0].shape == (8, 8, 3)
+    assert bar.updates == 6 and not bar.closed  # a supplied bar is not owned
+    assert [m.has_values for m in seen] == [False, True, False, True, False, True]
+    # frame bytes follow the reference: clamp -> *255 -> truncation
+    want = (x.detach().clamp(0, 1).squeeze(0).permute(1, 2, 0).numpy() * 255).astype("uint8")
+    assert np.array_equal(sink.frames[-1], want)
+
+
+def test_runner_multi_probe_one_frame_per_accepted_step() -> None:
+    x = _img()
+    sink, bar = Sink(), Bar()
+    runner = OptimizationRunner(TinyModel(), x, _cfg(steps=4, save_every=1),
+                                optimizer=MultiProbeSGD([x], lr=0.01), progress_bar=bar,
+                                video_writer=sink)
+    runner.run()
+    assert runner._closure_calls == 12 and bar.updates == 4 and len(sink.frames) == 4  # noqa: SLF001
+
+
+def test_runner_csv_logging_and_fallback(tmp_path: Path) -> None:
+    x = _img()
+    path = tmp_path / "loss.csv"
+    runner = OptimizationRunner(TinyModel(), x, _cfg(log_loss=str(path)),
+                                optimizer=torch.optim.Adam([x], lr=0.1), progress_bar=Bar())
+    _, hist, _ = runner.run()
+    assert hist == {}  # CSV replaces the in-memory history
+    rows = list(csv.reader(path.open()))
+    assert [r[0] for r in rows[1:]] == ["2", "4", "6"] and runner.loss_logger.file.closed
+    errors: list[Exception] = []
+    bad = tmp_path / "dir"
+    bad.mkdir()
+    x2 = _img()
+    runner2 = OptimizationRunner(TinyModel(), x2, _cfg(log_loss=str(bad)),
+                                 optimizer=torch.optim.Adam([x2], lr=0.1), progress_bar=Bar(),
+                                 callbacks=OptimizationCallbacks(on_logging_error=errors.append))
+    _, hist2, _ = runner2.run()
+    assert len(errors) == 1 and isinstance(errors[0], OSError) and len(hist2["total_loss"]) == 6
+
+
+def test_runner_argument_and_default_optimizer_rules() -> None:
+    x = _img()
+    with pytest.raises(ValueError, match="either optimizer or optimizer_factory"):
+        OptimizationRunner(TinyModel(), x, _cfg(), optimizer=torch.optim.Adam([x]),
+                           optimizer_factory=lambda p: torch.optim.Adam([p]))
+    cfg = _cfg()
+    cfg.optimization.lr = 0.5
+    cfg.optimization.lbfgs_max_iter = 3
+    r = OptimizationRunner(TinyModel(), x, cfg, progress_bar=Bar())
+    assert isinstance(r.optimizer, torch.optim.LBFGS)
+    assert r.optimizer.param_groups[0]["lr"] == 0.5 and r.optimizer.param_groups[0]["max_iter"] == 3
+    made = []
+    r2 = OptimizationRunner(TinyModel(), x, cfg, progress_bar=Bar(),
+                            optimizer_factory=lambda p: made.append(p) or torch.optim.SGD([p], lr=0.1))
+    assert made[0] is x and isinstance(r2.optimizer, torch.optim.SGD)
+    with pytest.raises(RuntimeError, match="Progress bar not initialized"):
+        _ = OptimizationRunner(TinyModel(), x, cfg, optimizer=torch.optim.SGD([x], lr=0.1)).progress_bar
+
+
+def test_runner_closure_after_completion_and_missing_metrics() -> None:
+    x = _img()
+    runner = OptimizationRunner(TinyModel(), x, _cfg(steps=2),
+                                optimizer=torch.optim.Adam([x], lr=0.1), progress_bar=Bar())
+    assert float(runner._final_loss_tensor()) == 0.0  # noqa: SLF001
+    runner.run()
+    calls = runner._closure_calls  # noqa: SLF001
+    again = runner._closure()  # noqa: SLF001
+    assert runner._closure_calls == calls + 1  # noqa: SLF001
+    assert float(again) == pytest.approx(float(runner._last_loss_tensor))  # noqa: SLF001
+
+    class NoClosure(torch.optim.SGD):
+        def step(self, closure=None):  # noqa: ANN001, ANN201
+            return None
+
+    x2 = _img()
+    bad = OptimizationRunner(TinyModel(), x2, _cfg(steps=1), optimizer=NoClosure([x2], lr=0.1),
+                             progress_bar=Bar())
+    with pytest.raises(RuntimeError, match="did not record metrics for step 1"):
+        bad.run()
+
+
+def test_runner_non_finite_warnings(caplog: pytest.LogCaptureFixture) -> None:
+    from style_transfer_visualizer_b200.logging_utils import logger
+
+    class NanModel(nn.Module):
+        def forward(self, x):  # noqa: ANN001, ANN201
+            return [x.mean() * float("nan")], [x.mean()]
+
+    x = _img()
+    runner = OptimizationRunner(NanModel(), x, _cfg(steps=1),
+                                optimizer=torch.optim.SGD([x], lr=0.0), progress_bar=Bar())
+    logger.propagate = True
+    try:
+        with caplog.at_level(logging.WARNING, logger="style_transfer"):
+            runner.run()
+    finally:
+        logger.propagate = False
+    assert "Non-finite style score at step 1" in caplog.text
+    assert "Non-finite total loss at step 1, using previous loss" in caplog.text
+    assert "Non-finite content score" not in caplog.text
+
+
+def test_runner_intro_crossfade_once() -> None:
+    x = _img()
+    sink = Sink()
+    intro = np.zeros((8, 8, 3), dtype=np.uint8)
+    runner = OptimizationRunner(TinyModel(), x, _cfg(steps=4, save_every=2),
+                                optimizer=torch.optim.Adam([x], lr=0.1), progress_bar=Bar(),
+                                video_writer=sink, intro_last_frame=intro, intro_crossfade_frames=3)
+    runner.run()
+    assert len(sink.frames) == 3 + 2 and runner.intro_transition_done
+    assert runner.intro_last_frame is None
+    blend = sink.frames[1].astype(int)
+    assert np.all(blend <= sink.frames[3].astype(int))  # halfway between black and frame 1
+
+
+def test_history_is_bounded(caplog: pytest.LogCaptureFixture) -> None:
+    x = torch.rand(1, 3, 2, 2).requires_grad_(True)
+    cfg = _cfg(steps=2100, save_every=5000, log_every=500)
+    runner = OptimizationRunner(TinyModel(), x, cfg, optimizer=torch.optim.SGD([x], lr=0.01),
+                                progress_bar=Bar())
+    _, hist, _ = runner.run()
+    assert len(hist["total_loss"]) == 2048

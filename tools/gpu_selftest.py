@@ -54,8 +54,9 @@ def case_elementwise() -> bool:
     # pack weights
     w = torch.randn(128, 64, 3, 3, device=dev, generator=g)
     wf, wd = ops.pack_conv_weights(w)
-    ok &= report("pack fwd", rel_l2(wf, w.permute(2, 3, 0, 1).reshape(9, 128, 64)), 0)
-    ok &= report("pack dgrad", rel_l2(wd, w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 64, 128)), 0)
+    ok &= report("pack fwd (tf32-rounded)", rel_l2(wf, w.permute(2, 3, 0, 1).reshape(9, 128, 64)), 3e-4)
+    ok &= report("pack fwd low bits zero", float((wf.view(torch.int32) & 0x1FFF).abs().max()), 0)
+    ok &= report("pack dgrad (tf32-rounded)", rel_l2(wd, w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 64, 128)), 3e-4)
 
     for (h, wdt) in [(64, 64), (33, 47), (135, 250)]:
         # first conv fwd
@@ -67,7 +68,7 @@ def case_elementwise() -> bool:
         ops.conv3x3_first_fwd(img, w1, b1, pre, post)
         ref = F.conv2d(img, w1, b1, padding=1)
         ok &= report(f"conv_first_fwd pre {h}x{wdt}", rel_l2(pre, nhwc(ref)), 2e-6)
-        ok &= report(f"conv_first_fwd post {h}x{wdt}", rel_l2(post, nhwc(ref.relu())), 2e-6)
+        ok &= report(f"conv_first_fwd post {h}x{wdt} (tf32-rounded)", rel_l2(post, nhwc(ref.relu())), 3e-4)
         # first conv dgrad
         dy = torch.randn(1, 64, h, wdt, device=dev, generator=g)
         dimg = torch.empty(1, 3, h, wdt, device=dev)
@@ -100,7 +101,7 @@ def case_elementwise() -> bool:
     dy = torch.randn_like(x)
     dx = torch.ones_like(x)
     ops.relu_bwd(dy, x, dx, accumulate=True)
-    ok &= report("relu bwd acc", rel_l2(dx, 1 + dy * (x > 0)), 0)
+    ok &= report("relu bwd acc (tf32-rounded)", rel_l2(dx, 1 + dy * (x > 0)), 3e-4)
 
     # content loss
     n = 512 * 33 * 47
@@ -114,7 +115,7 @@ def case_elementwise() -> bool:
     gw = torch.tensor([3.0], device=dev)
     df = torch.empty_like(f)
     ops.content_loss_bwd(f, t, gw, df, accumulate=False)
-    ok &= report("content bwd", rel_l2(df, 3.0 * 2 * (f - t) / n), 1e-6)
+    ok &= report("content bwd (tf32-rounded)", rel_l2(df, 3.0 * 2 * (f - t) / n), 3e-4)
 
     # adam vs torch.optim.Adam
     p = torch.randn(100003, device=dev, generator=g)
