@@ -158,17 +158,19 @@ def build_job(device, h: int, w: int, seed_offset: int):  # noqa: ANN001
     import torch
 
     import style_transfer_visualizer_b200.core_model as cm
-    from oracle import stv_oracle as orc  # input/weight generators shared with the CPU arm
+    from style_transfer_visualizer_b200 import synthetic
+    from style_transfer_visualizer_b200.constants import (DEFAULT_CONTENT_LAYERS,
+                                                          DEFAULT_STYLE_LAYERS)
 
     original = cm.initialize_vgg
-    cm.initialize_vgg = lambda: orc.vgg19_features(0)
+    cm.initialize_vgg = lambda: synthetic.random_vgg19_features(0)  # same seed as the CPU arm
     try:
-        model = cm.StyleContentModel(list(orc.DEFAULT_STYLE_LAYERS),
-                                     list(orc.DEFAULT_CONTENT_LAYERS)).to(device)
+        model = cm.StyleContentModel(list(DEFAULT_STYLE_LAYERS),
+                                     list(DEFAULT_CONTENT_LAYERS)).to(device)
     finally:
         cm.initialize_vgg = original
-    content = orc.synthetic_image(1 + 2 * seed_offset, h, w).pin_memory()
-    style = orc.synthetic_image(2 + 2 * seed_offset, h, w).pin_memory()
+    content = synthetic.synthetic_image(1 + 2 * seed_offset, h, w).pin_memory()
+    style = synthetic.synthetic_image(2 + 2 * seed_offset, h, w).pin_memory()
     torch.cuda.synchronize(device)
     return model, content, style
 
@@ -291,7 +293,7 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
     del launches_before
 
     # ---- end to end through the public API: pinned host inputs, H2D + per-step loss D2H -------
-    e2e_steps = min(k_steps, 100)
+    e2e_steps = k_steps
     torch.cuda.synchronize(device)
     jobs.barrier()
     t0 = time.perf_counter()

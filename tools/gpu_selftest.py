@@ -209,7 +209,8 @@ def case_conv() -> bool:
     # sanity of the on-device naive conv first (fp32 exact-ish)
     x, wt, b = _conv_inputs(20, 24, 64, 64, g, dev)
     wf, wd = ops.pack_conv_weights(wt)
-    ref = nhwc(F.conv2d(x, wt, b, padding=1))
+    wt_rounded = wf.reshape(3, 3, 64, 64).permute(2, 3, 0, 1).contiguous()  # packing rounds to tf32
+    ref = nhwc(F.conv2d(x, wt_rounded, b, padding=1))
     ok &= report("conv_ref vs torch", rel_l2(ops.conv_ref(nhwc(x), wf, b, taps=9, relu=False), ref), 5e-6)
 
     configs = [
