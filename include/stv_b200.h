@@ -60,6 +60,11 @@ int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int C
 int stv_conv3x3_first_dgrad(const float* dy, const float* w /*[64][3][3][3]*/, int H, int W,
                             int Cout, float* dimg_nchw, void* stream);
 
+/* Tensor-core variant of the above: w16_dgrad = [9][16][64] (rows 0..2 = the 3 image channels of
+ * the flipped/transposed packing, rows 3..15 zero; N is padded to the smallest UMMA width). */
+int stv_conv3x3_first_dgrad_tc(const float* dy, const float* w16_dgrad, int H, int W, int Cout,
+                               float* dimg_nchw, void* stream);
+
 /* ---- pooling / ReLU (torchvision MaxPool2d(2,2), nn.ReLU; core_model.py:134-135) ----------- */
 int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream);
 /* dx = route(dy) to the first max of each 2x2 window; relu_mask != 0 additionally gates by x > 0. */
@@ -129,6 +134,12 @@ int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C
                       const float* bias, const float* alpha, const float* mask_src,
                       const float* add_src, float* out_pre, float* out_post, int block_n, int th,
                       int tw, void* stream);
+/* Same for the persistent tap-reusing kernel: block_n in {64,128,256}, m_halves in {1,2} (128 or 256
+ * pixels per CTA), tw in {8,16,32}; 0 = auto. */
+int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                       const float* bias, const float* alpha, const float* mask_src,
+                       const float* add_src, float* out_pre, float* out_post, int block_n,
+                       int m_halves, int tw, void* stream);
 /* Naive CUDA-core NHWC conv, same packed weights; on-device cross-check only. */
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream);

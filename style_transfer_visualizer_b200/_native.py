@@ -30,6 +30,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_conv3x3_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "stv_conv3x3_dgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "stv_conv3x3_first_dgrad": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "stv_conv3x3_first_dgrad_tc": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "stv_maxpool2_fwd": [_vp, _i, _i, _i, _vp, _vp],
     "stv_maxpool2_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "stv_relu_fwd": [_vp, _l, _vp, _vp],
@@ -53,6 +54,8 @@ _SIGNATURES: dict[str, list] = {
     "stv_finite_flags": [_vp, _i, _vp, _vp],
     "stv_conv_igemm_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                           _vp],
+    "stv_conv_igemm2_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                           _vp],
     "stv_conv_ref": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"stv_gram_workspace_bytes": _sz}

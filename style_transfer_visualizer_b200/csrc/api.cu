@@ -1,6 +1,7 @@
 // C-ABI surface (include/stv_b200.h) over the kernel launchers, plus the shared host utilities:
 // thread-local error string, cached device properties and the TMA descriptor encoder.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/stv_b200.h"
@@ -96,6 +97,17 @@ static int check_device_impl() {
 using namespace stv;
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
+// STV_CONV_V1=1 routes the hot-path convolutions through the first-generation kernel
+// (conv_igemm.cu) for A/B measurements; the default is the persistent tap-reusing kernel.
+static bool use_conv_v1() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("STV_CONV_V1");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 extern "C" {
 
 const char* stv_last_error(void) { return last_error(); }
@@ -115,19 +127,38 @@ int stv_conv3x3_first_fwd(const float* img_nchw, const float* w, const float* bi
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
                     int Cout, float* out_pre, float* out_post, void* stream) {
   // out_post feeds the next conv's MMA -> stored tf32-rounded; out_pre (read by the losses) exact.
-  return conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
-                           out_post, 2, 0, 0, 0, S(stream));
+  if (use_conv_v1())
+    return conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr,
+                             out_pre, out_post, 2, 0, 0, 0, S(stream));
+  return conv_igemm2_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
+                            out_post, 2, nullptr, 0, 0, 0, S(stream));
 }
 
 int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                       const float* relu_src, int accumulate, float* dx, void* stream) {
-  return conv_igemm_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
-                           accumulate ? dx : nullptr, dx, nullptr, 1, 0, 0, 0, S(stream));
+  if (use_conv_v1())
+    return conv_igemm_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
+                             accumulate ? dx : nullptr, dx, nullptr, 1, 0, 0, 0, S(stream));
+  return conv_igemm2_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
+                            accumulate ? dx : nullptr, dx, nullptr, 1, nullptr, 0, 0, 0, S(stream));
 }
 
 int stv_conv3x3_first_dgrad(const float* dy, const float* w, int H, int W, int Cout,
                             float* dimg_nchw, void* stream) {
   return conv_first_dgrad_launch(dy, w, H, W, Cout, dimg_nchw, S(stream));
+}
+int stv_conv3x3_first_dgrad_tc(const float* dy, const float* w16_dgrad, int H, int W, int Cout,
+                               float* dimg_nchw, void* stream) {
+  // STV_FD_MH / STV_FD_TW: tile overrides for experiments
+  static int mh = -1, tw = -1;
+  if (mh < 0) {
+    const char* a = getenv("STV_FD_MH");
+    const char* b = getenv("STV_FD_TW");
+    mh = a ? atoi(a) : 0;
+    tw = b ? atoi(b) : 0;
+  }
+  return conv_igemm2_launch(dy, w16_dgrad, H, W, Cout, 16, 9, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, 0, dimg_nchw, 0, mh, tw, S(stream));
 }
 
 int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream) {
@@ -159,6 +190,16 @@ int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* g
   // dY[p, :] = grad_w * X[p, :] * S  -- a 1x1 "conv" over a (1 x hw) image with weight matrix S
   // (symmetric, so its rows serve directly as the K-major B operand).
   STV_REQUIRE(hw <= 0x7fffffffL, "style_bwd: feature map too large");
+  if (!use_conv_v1()) {
+    // 1x1: view the feature map as a (hw/32 x 32) image when possible so that 2-D patches apply
+    int h2 = 1, w2 = static_cast<int>(hw);
+    if (hw % 32 == 0) { h2 = static_cast<int>(hw / 32); w2 = 32; }
+    else if (hw % 16 == 0) { h2 = static_cast<int>(hw / 16); w2 = 16; }
+    else if (hw % 8 == 0) { h2 = static_cast<int>(hw / 8); w2 = 8; }
+    return conv_igemm2_launch(x, s, h2, w2, C, C, 1, nullptr, grad_w, nullptr,
+                              accumulate ? dy : nullptr, dy, nullptr, 1, nullptr, 0, 0, 0,
+                              S(stream));
+  }
   return conv_igemm_launch(x, s, 1, static_cast<int>(hw), C, C, 1, nullptr, grad_w, nullptr,
                            accumulate ? dy : nullptr, dy, nullptr, 1, 0, 1, 128, S(stream));
 }
@@ -216,6 +257,13 @@ int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C
                       int tw, void* stream) {
   return conv_igemm_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
                            out_post, 0, block_n, th, tw, S(stream));
+}
+int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                       const float* bias, const float* alpha, const float* mask_src,
+                       const float* add_src, float* out_pre, float* out_post, int block_n,
+                       int m_halves, int tw, void* stream) {
+  return conv_igemm2_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
+                            out_post, 0, nullptr, block_n, m_halves, tw, S(stream));
 }
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream) {

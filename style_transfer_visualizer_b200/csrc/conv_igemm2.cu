@@ -1,0 +1,428 @@
+// Tensor-core 3x3 / 1x1 convolution, version 2: persistent, tap-reusing implicit GEMM.
+//
+// Same math and epilogue options as conv_igemm.cu (which it supersedes on the hot path); the
+// difference is how operands reach shared memory.  Version 1 is bound by L2->SM bandwidth: every
+// K step (one tap x 32 channels) re-loads a 128-pixel A tile and a BLOCK_N weight tile, i.e.
+// (128 + BLOCK_N) * 128 bytes per 2*128*BLOCK_N*32 FLOP, which is 11-14 TB/s at the rates measured.
+// Here:
+//   * one A stage is a TALL patch {32 ch, tw, TH + 2 rows} loaded once per (channel slab, dx) and
+//     used by the three dy taps through row-shifted UMMA descriptors.  With tw a multiple of 8
+//     every 8-row core-matrix group is one 1024-byte-aligned run of 8 pixels, so the shifted views
+//     keep the canonical K-major SWIZZLE_128B layout (SBO = 1024) -- A traffic drops 3x;
+//   * a CTA owns M = 256 pixels (two 128-row accumulators in TMEM) that share every weight stage
+//     -- B traffic per FLOP halves;
+//   * the kernel is persistent (one CTA per SM, static tile schedule, n-tile-major so concurrent
+//     CTAs share weights in L2); operand rings keep streaming across tile boundaries and, when TMEM
+//     allows (2 * M_HALVES * BLOCK_N <= 512 columns), the accumulator is double-buffered so the
+//     epilogue of tile i overlaps the main loop of tile i+1.
+// Also hosts the N = 16 variant used for conv1_1's input gradient (64 -> 3 channels, written as
+// NCHW planes): the 3 real output channels are padded to the smallest legal UMMA N.
+#include "stv_common.cuh"
+#include "stv_kernels.h"
+
+namespace stv {
+
+struct Conv2Params {
+  int H, W, C, N;
+  int taps;            // 9 or 1
+  int tw, th;          // CTA patch: th * tw == 128 * M_HALVES
+  int tw_shift;        // log2(tw)
+  int tiles_x, tiles_m, tiles_total;
+  int a_stage_bytes;   // (th + ndy - 1) * tw * 128, multiple of 1024
+  const float* bias;
+  const float* alpha;
+  const float* mask_src;
+  const float* add_src;
+  float* out_pre;
+  float* out_post;
+  int round_pre, round_post;
+  float* out_nchw3;    // N == 16 variant: [3][H][W] planes
+};
+
+constexpr int kThreads2 = 192;
+
+template <int BLOCK_N, int MH, int AS, int BS>
+struct Conv2Cfg {
+  static constexpr int kAcc = (2 * MH * BLOCK_N <= 512) ? 2 : 1;
+  static constexpr int kTmemColsRaw = kAcc * MH * BLOCK_N;
+  static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kNumBars = 2 * AS + 2 * BS + 2 * kAcc;
+};
+
+template <int BLOCK_N, int MH, int AS, int BS>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                        const __grid_constant__ CUtensorMap tmap_w, const Conv2Params p) {
+  using Cfg = Conv2Cfg<BLOCK_N, MH, AS, BS>;
+  constexpr int kAcc = Cfg::kAcc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + AS * p.a_stage_bytes;
+  const uint32_t bar_base = b_base + BS * Cfg::kBBytes;
+  const uint32_t a_full = bar_base, a_empty = a_full + 8 * AS;
+  const uint32_t b_full = a_empty + 8 * AS, b_empty = b_full + 8 * BS;
+  const uint32_t acc_full = b_empty + 8 * BS, acc_empty = acc_full + 8 * kAcc;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + (bar_base - smem_base) + 8 * Cfg::kNumBars);
+  // bias for all N output channels, staged once (epilogue reads it as smem broadcasts)
+  float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * Cfg::kNumBars + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kc = p.C >> 5;
+  const int ndx = p.taps == 9 ? 3 : 1;
+  const int ndy = ndx;
+  const int row_bytes = p.tw * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < kAcc; ++s) { mbar_init(acc_full + 8 * s, 1); mbar_init(acc_empty + 8 * s, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp >= 2 && BLOCK_N != 16) {
+    for (int i = threadIdx.x - 64; i < p.N; i += kThreads2 - 64)
+      sbias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer --------------------------------------------
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        const int nt = t / p.tiles_m, mt = t - nt * p.tiles_m;
+        const int ty0 = (mt / p.tiles_x) * p.th, tx0 = (mt % p.tiles_x) * p.tw;
+        const int n0 = nt * BLOCK_N;
+        for (int c = 0; c < kc; ++c) {
+          for (int dxi = 0; dxi < ndx; ++dxi) {
+            mbar_wait(a_empty + 8 * as, aph ^ 1);
+            mbar_expect_tx(a_full + 8 * as, p.a_stage_bytes);
+            tma_load_3d(a_base + as * p.a_stage_bytes, &tmap_x, a_full + 8 * as, c << 5,
+                        tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+            if (++as == AS) { as = 0; aph ^= 1; }
+            for (int dyi = 0; dyi < ndy; ++dyi) {
+              const int tap = dyi * ndx + dxi;
+              mbar_wait(b_empty + 8 * bs, bph ^ 1);
+              mbar_expect_tx(b_full + 8 * bs, Cfg::kBBytes);
+              tma_load_2d(b_base + bs * Cfg::kBBytes, &tmap_w, b_full + 8 * bs, c << 5,
+                          tap * p.N + n0);
+              if (++bs == BS) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer -----------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, accph = 0;
+      const uint32_t half_bytes = (128 >> p.tw_shift) * row_bytes;  // rows per 128-pixel half
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        mbar_wait(acc_empty + 8 * acc, accph ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (MH * BLOCK_N);
+        uint32_t first = 1;
+        for (int c = 0; c < kc; ++c) {
+          for (int dxi = 0; dxi < ndx; ++dxi) {
+            mbar_wait(a_full + 8 * as, aph);
+            const uint32_t a_addr = a_base + as * p.a_stage_bytes;
+            for (int dyi = 0; dyi < ndy; ++dyi) {
+              mbar_wait(b_full + 8 * bs, bph);
+              tc_fence_after();
+              const uint32_t b_addr = b_base + bs * Cfg::kBBytes;
+#pragma unroll
+              for (int hf = 0; hf < MH; ++hf) {
+                const uint32_t a_view = a_addr + dyi * row_bytes + hf * half_bytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_tf32(d0 + hf * BLOCK_N, make_smem_desc_sw128(a_view + k * 32, 16, 1024),
+                            make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
+                            (first && k == 0) ? 0u : 1u);
+                }
+              }
+              first = 0;
+              umma_commit(b_empty + 8 * bs);
+              if (++bs == BS) { bs = 0; bph ^= 1; }
+            }
+            umma_commit(a_empty + 8 * as);
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+        }
+        umma_commit(acc_full + 8 * acc);
+        if (++acc == kAcc) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue -------------------------------------------------
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t accph = 0;
+    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+      const int nt = t / p.tiles_m, mt = t - nt * p.tiles_m;
+      const int ty0 = (mt / p.tiles_x) * p.th, tx0 = (mt % p.tiles_x) * p.tw;
+      const int n0 = nt * BLOCK_N;
+      mbar_wait(acc_full + 8 * acc, accph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hf = 0; hf < MH; ++hf) {
+        const int m = hf * 128 + q * 32 + lane;
+        const int py = ty0 + (m >> p.tw_shift);
+        const int px = tx0 + (m & (p.tw - 1));
+        const bool valid = (py < p.H) && (px < p.W);
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                              acc * (MH * BLOCK_N) + hf * BLOCK_N;
+        if constexpr (BLOCK_N == 16) {
+          uint32_t r[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+                "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(trow)
+              : "memory");
+          tmem_ld_wait();
+          if (valid) {
+            const size_t hw = static_cast<size_t>(p.H) * p.W;
+            const size_t o = static_cast<size_t>(py) * p.W + px;
+            p.out_nchw3[o] = __uint_as_float(r[0]);
+            p.out_nchw3[hw + o] = __uint_as_float(r[1]);
+            p.out_nchw3[2 * hw + o] = __uint_as_float(r[2]);
+          }
+        } else {
+          const size_t row_off = (static_cast<size_t>(py) * p.W + px) * p.N + n0;
+#pragma unroll 1
+          for (int cb = 0; cb < BLOCK_N; cb += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + cb, r);  // asynchronous until tmem_ld_wait()
+            // issue every global load of this 32-channel chunk before touching the results, so
+            // their latencies overlap each other and the TMEM read
+            float4 mk[8], ad[8];
+            const bool use_mask = valid && p.mask_src != nullptr;
+            const bool use_add = valid && p.add_src != nullptr;
+            if (use_mask) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                mk[j] = __ldg(reinterpret_cast<const float4*>(p.mask_src + row_off + cb) + j);
+            }
+            if (use_add) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                ad[j] = *(reinterpret_cast<const float4*>(p.add_src + row_off + cb) + j);
+            }
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + cb + 4 * j);
+                float4 v;
+                v.x = fmaf(__uint_as_float(r[4 * j + 0]), alpha, b.x);
+                v.y = fmaf(__uint_as_float(r[4 * j + 1]), alpha, b.y);
+                v.z = fmaf(__uint_as_float(r[4 * j + 2]), alpha, b.z);
+                v.w = fmaf(__uint_as_float(r[4 * j + 3]), alpha, b.w);
+                if (use_mask) {
+                  v.x = mk[j].x > 0.f ? v.x : 0.f;
+                  v.y = mk[j].y > 0.f ? v.y : 0.f;
+                  v.z = mk[j].z > 0.f ? v.z : 0.f;
+                  v.w = mk[j].w > 0.f ? v.w : 0.f;
+                }
+                if (use_add) {
+                  v.x += ad[j].x; v.y += ad[j].y; v.z += ad[j].z; v.w += ad[j].w;
+                }
+                const int col = cb + 4 * j;
+                if (p.out_pre) {
+                  float4 o = v;
+                  if (p.round_pre) {
+                    o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+                    o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+                  }
+                  *reinterpret_cast<float4*>(p.out_pre + row_off + col) = o;
+                }
+                if (p.out_post) {
+                  float4 o;
+                  o.x = fmaxf(v.x, 0.f); o.y = fmaxf(v.y, 0.f);
+                  o.z = fmaxf(v.z, 0.f); o.w = fmaxf(v.w, 0.f);
+                  if (p.round_post) {
+                    o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+                    o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+                  }
+                  *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * acc);
+      if (++acc == kAcc) { acc = 0; accph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int MH, int AS, int BS>
+static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Params& p, int grid,
+                   cudaStream_t stream) {
+  using Cfg = Conv2Cfg<BLOCK_N, MH, AS, BS>;
+  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, AS, BS>;
+  const int smem = AS * p.a_stage_bytes + BS * Cfg::kBBytes + 8 * Cfg::kNumBars + 32 + 1024 +
+                   p.N * 4;
+  STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    STV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024));
+    attr_smem = 227 * 1024;
+  }
+  kern<<<grid, kThreads2, smem, stream>>>(tx, tw, p);
+  STV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Tile selection (measured on B200, profiles/r1_selftest_perf_v2.log): N tile as wide as Cout
+// allows; 256-wide tiles run best with one 128-pixel half per CTA (double-buffered accumulator),
+// narrower tiles with two halves sharing each weight stage.  When that leaves SMs idle the tile is
+// narrowed.  tw is the patch width with the least padded area (ties: wider rows = smaller halo).
+struct TileChoice { int mh, tw, th, block_n; };
+
+static long count_tiles(int H, int W, int N, int mh, int tw, int bn) {
+  const int th = 128 * mh / tw;
+  return static_cast<long>((H + th - 1) / th) * ((W + tw - 1) / tw) * (N / bn);
+}
+
+static int pick_tw(int H, int W, int mh) {
+  // least padded pixels (= MMA work); the dy halo only inflates A traffic, so it is a tie-breaker
+  const int tw_opts[3] = {16, 32, 8};
+  int best = 16;
+  double best_cost = -1.0;
+  for (int i = 0; i < 3; ++i) {
+    const int tw = tw_opts[i], th = 128 * mh / tw;
+    const double area = static_cast<double>((H + th - 1) / th) * th * (((W + tw - 1) / tw) * tw);
+    const double cost = area * (1.0 + 0.15 * 2.0 / th);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = tw;
+    }
+  }
+  return best;
+}
+
+static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int force_n, int force_mh,
+                               int force_tw) {
+  (void)taps;
+  const int sms = device_sm_count();
+  int bn, mh;
+  if (N == 16) { bn = 16; mh = 1; }
+  else if (N % 256 == 0) { bn = 256; mh = C >= 512 ? 2 : 1; }
+  else if (N % 128 == 0) { bn = 128; mh = 2; }
+  else { bn = 64; mh = 1; }
+  if (force_n <= 0 && force_mh <= 0 && N != 16) {
+    // keep the machine busy on small feature maps: narrow the tile until ~every SM has one
+    const int order[5][2] = {{256, 2}, {256, 1}, {128, 2}, {128, 1}, {64, 1}};
+    int i = 0;
+    while (i < 5 && !(order[i][0] == bn && order[i][1] == mh)) ++i;
+    while (i < 4) {
+      const int tw = pick_tw(H, W, mh);
+      if (count_tiles(H, W, N, mh, tw, bn) >= (3L * sms) / 4) break;
+      ++i;
+      if (N % order[i][0] != 0) continue;
+      bn = order[i][0];
+      mh = order[i][1];
+    }
+  }
+  if (force_n > 0) bn = force_n;
+  if (force_mh > 0) mh = force_mh;
+  const int tw = force_tw > 0 ? force_tw : pick_tw(H, W, mh);
+  return TileChoice{mh, tw, 128 * mh / tw, bn};
+}
+
+int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                       const float* bias, const float* alpha, const float* mask_src,
+                       const float* add_src, float* out_pre, float* out_post, int round_flags,
+                       float* out_nchw3, int force_n, int force_mh, int force_tw,
+                       cudaStream_t stream) {
+  STV_REQUIRE(C % 32 == 0 && C >= 32, "conv_igemm2: input channels %d must be a multiple of 32", C);
+  STV_REQUIRE(N % 64 == 0 || N == 16, "conv_igemm2: output channels %d must be 16 or a multiple of 64", N);
+  STV_REQUIRE(taps == 9 || taps == 1, "conv_igemm2: taps must be 9 or 1 (got %d)", taps);
+  STV_REQUIRE(H > 0 && W > 0, "conv_igemm2: empty image");
+  STV_REQUIRE((N == 16) == (out_nchw3 != nullptr), "conv_igemm2: N == 16 <=> NCHW3 output");
+  STV_REQUIRE(out_pre || out_post || out_nchw3, "conv_igemm2: no output buffer");
+
+  const TileChoice tc = choose_tiles(H, W, C, N, taps, force_n, force_mh, force_tw);
+  Conv2Params p;
+  p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps;
+  p.tw = tc.tw; p.th = tc.th;
+  p.tw_shift = tc.tw == 8 ? 3 : (tc.tw == 16 ? 4 : 5);
+  p.tiles_x = (W + tc.tw - 1) / tc.tw;
+  p.tiles_m = p.tiles_x * ((H + tc.th - 1) / tc.th);
+  p.tiles_total = p.tiles_m * (N / tc.block_n);
+  const int halo = taps == 9 ? 2 : 0;
+  p.a_stage_bytes = (tc.th + halo) * tc.tw * 128;
+  p.bias = bias; p.alpha = alpha; p.mask_src = mask_src; p.add_src = add_src;
+  p.out_pre = out_pre; p.out_post = out_post;
+  p.round_pre = round_flags & 1; p.round_post = (round_flags >> 1) & 1;
+  p.out_nchw3 = out_nchw3;
+
+  CUtensorMap tx, twm;
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)H};
+    const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)W * C * 4};
+    const uint32_t box[3] = {32, (uint32_t)tc.tw, (uint32_t)(tc.th + halo)};
+    if (int rc = encode_tmap_f32(&tx, x, 3, dims, strides, box, kSwizzle128B)) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)taps * N};
+    const uint64_t strides[1] = {(uint64_t)C * 4};
+    const uint32_t box[2] = {32, (uint32_t)tc.block_n};
+    if (int rc = encode_tmap_f32(&twm, w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
+  }
+  const int sms = device_sm_count();
+  const int as_n = tc.block_n >= 256 ? 2 : 3;
+  const int smem_est = as_n * p.a_stage_bytes + 4 * tc.block_n * 128 + 2048 + N * 4;
+  const int ctas_per_sm = smem_est <= 110 * 1024 ? 2 : 1;  // TMEM: <= 256 columns each
+  const int grid = p.tiles_total < sms * ctas_per_sm ? p.tiles_total : sms * ctas_per_sm;
+
+#define STV_L2(BN, MHV, ASV, BSV) return launch2<BN, MHV, ASV, BSV>(tx, twm, p, grid, stream)
+  if (tc.block_n == 256 && tc.mh == 2) STV_L2(256, 2, 2, 4);
+  if (tc.block_n == 256 && tc.mh == 1) STV_L2(256, 1, 2, 4);
+  if (tc.block_n == 128 && tc.mh == 2) STV_L2(128, 2, 3, 4);
+  if (tc.block_n == 128 && tc.mh == 1) STV_L2(128, 1, 3, 4);
+  if (tc.block_n == 64 && tc.mh == 2) STV_L2(64, 2, 3, 4);
+  if (tc.block_n == 64 && tc.mh == 1) STV_L2(64, 1, 3, 4);
+  if (tc.block_n == 16 && tc.mh == 2) STV_L2(16, 2, 3, 4);
+  if (tc.block_n == 16 && tc.mh == 1) STV_L2(16, 1, 3, 4);
+#undef STV_L2
+  set_error("conv_igemm2: no kernel for N tile %d / M halves %d", tc.block_n, tc.mh);
+  return 2;
+}
+
+}  // namespace stv

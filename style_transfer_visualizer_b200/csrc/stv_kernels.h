@@ -13,6 +13,13 @@ int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C
                       const float* add_src, float* out_pre, float* out_post, int round_flags,
                       int block_n, int th, int tw, cudaStream_t stream);
 
+// conv_igemm2.cu (persistent, tap-reusing version; N == 16 writes NCHW 3-channel planes) ---------
+int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
+                       const float* bias, const float* alpha, const float* mask_src,
+                       const float* add_src, float* out_pre, float* out_post, int round_flags,
+                       float* out_nchw3, int force_n, int force_mh, int force_tw,
+                       cudaStream_t stream);
+
 // gram.cu ---------------------------------------------------------------------------------
 size_t gram_workspace_bytes(long hw, int C);
 int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,

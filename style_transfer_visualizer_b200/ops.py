@@ -66,6 +66,22 @@ def conv3x3_first_dgrad(dy: torch.Tensor, w: torch.Tensor, dimg: torch.Tensor) -
              _s(dy))
 
 
+def pack_first_dgrad_weights(w: torch.Tensor) -> torch.Tensor:
+    """conv1_1 weights ``[64, 3, 3, 3]`` -> ``[9, 16, 64]`` for the tensor-core input gradient
+    (flipped/transposed packing, 3 real rows padded to the smallest UMMA N)."""
+    _wf, wd = pack_conv_weights(w)          # wd: [9, 3, 64], tf32-rounded
+    out = torch.zeros(9, 16, w.shape[0], device=w.device, dtype=torch.float32)
+    out[:, :3, :] = wd
+    return out
+
+
+def conv3x3_first_dgrad_tc(dy: torch.Tensor, w16: torch.Tensor, dimg: torch.Tensor) -> None:
+    _chk(dy, "dy")
+    h, wd, cout = dy.shape
+    nat.call("stv_conv3x3_first_dgrad_tc", nat.ptr(dy), nat.ptr(w16), h, wd, cout, nat.ptr(dimg),
+             _s(dy))
+
+
 def maxpool2_fwd(x: torch.Tensor, y: torch.Tensor) -> None:
     _chk(x, "x")
     h, wd, c = x.shape
@@ -206,6 +222,19 @@ def conv_igemm_ex(x: torch.Tensor, w_packed: torch.Tensor, *, taps: int,  # noqa
     nat.call("stv_conv_igemm_ex", nat.ptr(x), nat.ptr(w_packed), h, wd, c, n, taps, nat.ptr(bias),
              nat.ptr(alpha), nat.ptr(mask_src), nat.ptr(add_src), nat.ptr(out_pre),
              nat.ptr(out_post), block_n, th, tw, _s(x))
+
+
+def conv_igemm2_ex(x: torch.Tensor, w_packed: torch.Tensor, *, taps: int,  # noqa: PLR0913
+                   bias: torch.Tensor | None = None, alpha: torch.Tensor | None = None,
+                   mask_src: torch.Tensor | None = None, add_src: torch.Tensor | None = None,
+                   out_pre: torch.Tensor | None = None, out_post: torch.Tensor | None = None,
+                   block_n: int = 0, m_halves: int = 0, tw: int = 0) -> None:
+    """Test hook: the persistent tap-reusing conv with explicit tile selection."""
+    h, wd, c = x.shape
+    n = w_packed.shape[-2]
+    nat.call("stv_conv_igemm2_ex", nat.ptr(x), nat.ptr(w_packed), h, wd, c, n, taps,
+             nat.ptr(bias), nat.ptr(alpha), nat.ptr(mask_src), nat.ptr(add_src), nat.ptr(out_pre),
+             nat.ptr(out_post), block_n, m_halves, tw, _s(x))
 
 
 def conv_ref(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None, *, taps: int,

@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-CASES = ["elementwise", "conv", "conv_variants", "gram", "perf"]
+CASES = ["elementwise", "conv", "conv2", "conv_variants", "gram", "perf"]
 
 
 def rel_l2(a, b):  # noqa: ANN001, ANN201
@@ -252,6 +252,80 @@ def case_conv() -> bool:
     return ok
 
 
+def case_conv2() -> bool:
+    """Persistent tap-reusing kernel (conv_igemm2): forced tile shapes, auto selection, 1x1,
+    epilogue options, and the N=16 first-layer input gradient."""
+    import torch
+    import torch.nn.functional as F  # noqa: N812
+
+    from style_transfer_visualizer_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ok = True
+    configs = [
+        # h, w, cin, cout, block_n, m_halves, tw
+        (16, 16, 64, 64, 64, 1, 8),
+        (16, 16, 64, 64, 64, 1, 16),
+        (16, 16, 64, 64, 64, 1, 32),
+        (32, 16, 64, 64, 64, 2, 8),
+        (32, 32, 64, 128, 128, 2, 16),
+        (40, 72, 128, 256, 256, 2, 8),
+        (40, 72, 128, 256, 256, 1, 16),
+        (33, 47, 128, 128, 128, 2, 8),     # ragged edges
+        (33, 47, 64, 64, 64, 2, 32),
+        (67, 120, 512, 512, 256, 2, 8),
+        (67, 120, 512, 512, 0, 0, 0),      # auto
+        (135, 240, 256, 512, 0, 0, 0),
+        (64, 64, 512, 512, 0, 0, 0),
+        (270, 480, 64, 64, 0, 0, 0),       # many tiles per CTA (persistent loop, acc double buffer)
+        (200, 300, 128, 128, 0, 0, 0),
+    ]
+    for (h, w, cin, cout, bn, mh, tw) in configs:
+        x, wt, b = _conv_inputs(h, w, cin, cout, g, dev)
+        wf, wd = ops.pack_conv_weights(wt)
+        ref = nhwc(F.conv2d(x, wt, b, padding=1))
+        pre = torch.full((h, w, cout), float("nan"), device=dev)
+        post = torch.full((h, w, cout), float("nan"), device=dev)
+        ops.conv_igemm2_ex(nhwc(x), wf, taps=9, bias=b, out_pre=pre, out_post=post, block_n=bn,
+                           m_halves=mh, tw=tw)
+        torch.cuda.synchronize()
+        tag = f"{h}x{w} {cin}->{cout} bn={bn} mh={mh} tw={tw}"
+        ok &= report(f"igemm2 fwd pre  {tag}", rel_l2(pre, ref), 2e-3)
+        ok &= report(f"igemm2 fwd post {tag}", rel_l2(post, ref.relu()), 2e-3)
+    # hot-path entry points (auto tiles): fwd, dgrad with gate + accumulate, style bwd, first dgrad
+    h, w, cin, cout = 37, 53, 128, 64
+    x, wt, b = _conv_inputs(h, w, cin, cout, g, dev)
+    wf, wd = ops.pack_conv_weights(wt)
+    dy = torch.randn(1, cout, h, w, device=dev, generator=g)
+    act = torch.randn(h, w, cin, device=dev, generator=g)
+    prev = torch.randn(h, w, cin, device=dev, generator=g)
+    refd = nhwc(torch.nn.grad.conv2d_input(x.shape, wt, dy, padding=1))
+    dx = prev.clone()
+    ops.conv3x3_dgrad(nhwc(dy), wd, dx, relu_src=act, accumulate=True)
+    ok &= report("igemm2 dgrad + relu gate + accumulate", rel_l2(dx, refd * (act > 0) + prev), 2e-3)
+    for (hh, ww) in [(64, 64), (33, 47), (135, 250)]:
+        w1 = torch.randn(64, 3, 3, 3, device=dev, generator=g) * 0.2
+        dy1 = torch.randn(1, 64, hh, ww, device=dev, generator=g)
+        ref1 = torch.nn.grad.conv2d_input((1, 3, hh, ww), w1, dy1, padding=1)
+        dimg = torch.full((1, 3, hh, ww), float("nan"), device=dev)
+        ops.conv3x3_first_dgrad_tc(nhwc(dy1), ops.pack_first_dgrad_weights(w1), dimg)
+        ok &= report(f"first dgrad (tensor core, N=16) {hh}x{ww}", rel_l2(dimg, ref1), 2e-3)
+    for c, hw in ((64, 33 * 47), (128, 64 * 64), (512, 67 * 120), (256, 1024 * 8 + 8)):
+        xf = torch.randn(hw, c, device=dev, generator=g)
+        sm = torch.randn(c, c, device=dev, generator=g)
+        sm = (sm + sm.t()) * 0.5
+        gw = torch.tensor([2.0], device=dev)
+        out = torch.randn(hw, c, device=dev, generator=g)
+        base = out.clone()
+        ops.style_bwd(xf, sm, gw, out, accumulate=True)
+        ok &= report(f"igemm2 style_bwd C={c} hw={hw}", rel_l2(out, base + 2.0 * (xf.double() @ sm.double()).float()), 2e-3)
+    torch.cuda.synchronize()
+    return ok
+
+
 def case_conv_variants() -> bool:
     import torch
     import torch.nn.functional as F  # noqa: N812
@@ -396,7 +470,23 @@ def case_perf() -> bool:
             if cout % bn:
                 continue
             ms2 = _time(lambda: ops.conv_igemm_ex(x, wf, taps=9, bias=b, out_post=post, block_n=bn))  # noqa: B023
-            line += f" | bn{bn} {ms2:.3f} ms {flops / ms2 / 1e9:.1f}"
+            line += f" | v1 bn{bn} {flops / ms2 / 1e9:.0f}"
+        for bn in (64, 128, 256):
+            if cout % bn:
+                continue
+            for mh in (1, 2):
+                for tw in (8, 16, 32):
+                    try:
+                        ms2 = _time(lambda: ops.conv_igemm2_ex(x, wf, taps=9, bias=b, out_post=post, block_n=bn, m_halves=mh, tw=tw))  # noqa: B023
+                        line += f" | v2 n{bn}m{mh}w{tw} {flops / ms2 / 1e9:.0f}"
+                    except Exception:  # noqa: BLE001
+                        line += f" | v2 n{bn}m{mh}w{tw} n/a"
+        if cin % 64 == 0:
+            dyb = torch.randn(h, w, cout, device=dev, generator=g)
+            dxb = torch.zeros(h, w, cin, device=dev)
+            act = torch.randn(h, w, cin, device=dev, generator=g)
+            ms4 = _time(lambda: ops.conv3x3_dgrad(dyb, wd, dxb, relu_src=act, accumulate=True))  # noqa: B023
+            line += f" | dgrad+gate+acc auto {ms4:.3f} ms {flops / ms4 / 1e9:.0f}"
         xt = x.permute(2, 0, 1).unsqueeze(0).contiguous(memory_format=torch.channels_last)
         wcl = wt.contiguous(memory_format=torch.channels_last)
         ms3 = _time(lambda: F.relu(F.conv2d(xt, wcl, b, padding=1)))  # noqa: B023
@@ -438,6 +528,9 @@ def case_perf() -> bool:
     dimg = torch.empty_like(img)
     ms = _time(lambda: ops.conv3x3_first_dgrad(pre, w1, dimg))
     print(f"PERF conv_first_dgrad 1080p: {ms:.3f} ms {(pre.numel() + img.numel()) * 4 / ms / 1e6:.0f} GB/s")
+    w16 = ops.pack_first_dgrad_weights(w1)
+    ms = _time(lambda: ops.conv3x3_first_dgrad_tc(pre, w16, dimg))
+    print(f"PERF conv_first_dgrad_tc 1080p: {ms:.3f} ms {(pre.numel() + img.numel()) * 4 / ms / 1e6:.0f} GB/s")
     p = img.flatten().clone()
     gr = torch.randn_like(p)
     m = torch.zeros_like(p)
