@@ -17,6 +17,8 @@
 //     epilogue of tile i overlaps the main loop of tile i+1.
 // Also hosts the N = 16 variant used for conv1_1's input gradient (64 -> 3 channels, written as
 // NCHW planes): the 3 real output channels are padded to the smallest legal UMMA N.
+#include <stdlib.h>
+
 #include "stv_common.cuh"
 #include "stv_kernels.h"
 
@@ -29,6 +31,9 @@ struct Conv2Params {
   int tw_shift;        // log2(tw)
   int tiles_x, tiles_m, tiles_total;
   int a_stage_bytes;   // (th + ndy - 1) * tw * 128, multiple of 1024
+  int a_stages, b_stages;  // ring depths
+  int tps;                 // weight taps per B stage (1 or 3): narrow N tiles batch the three dy taps
+                           // of one dx into a stage so the MMA thread synchronises 3x less often
   const float* bias;
   const float* alpha;
   const float* mask_src;
@@ -41,34 +46,35 @@ struct Conv2Params {
 
 constexpr int kThreads2 = 192;
 
-template <int BLOCK_N, int MH, int AS, int BS>
+template <int BLOCK_N, int MH>
 struct Conv2Cfg {
   static constexpr int kAcc = (2 * MH * BLOCK_N <= 512) ? 2 : 1;
   static constexpr int kTmemColsRaw = kAcc * MH * BLOCK_N;
   static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
   static constexpr int kBBytes = BLOCK_N * 128;
-  static constexpr int kNumBars = 2 * AS + 2 * BS + 2 * kAcc;
 };
 
-template <int BLOCK_N, int MH, int AS, int BS>
+template <int BLOCK_N, int MH, int TPS>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                         const __grid_constant__ CUtensorMap tmap_w, const Conv2Params p) {
-  using Cfg = Conv2Cfg<BLOCK_N, MH, AS, BS>;
+  using Cfg = Conv2Cfg<BLOCK_N, MH>;
   constexpr int kAcc = Cfg::kAcc;
+  const int AS = p.a_stages, BS = p.b_stages;
+  const int num_bars = 2 * AS + 2 * BS + 2 * kAcc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + AS * p.a_stage_bytes;
-  const uint32_t bar_base = b_base + BS * Cfg::kBBytes;
+  const uint32_t bar_base = b_base + BS * TPS * Cfg::kBBytes;
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * AS;
   const uint32_t b_full = a_empty + 8 * AS, b_empty = b_full + 8 * BS;
   const uint32_t acc_full = b_empty + 8 * BS, acc_empty = acc_full + 8 * kAcc;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + (bar_base - smem_base) + 8 * Cfg::kNumBars);
+      smem_gen + (bar_base - smem_base) + 8 * num_bars);
   // bias for all N output channels, staged once (epilogue reads it as smem broadcasts)
-  float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * Cfg::kNumBars + 16);
+  float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * num_bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,12 +120,15 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             tma_load_3d(a_base + as * p.a_stage_bytes, &tmap_x, a_full + 8 * as, c << 5,
                         tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
             if (++as == AS) { as = 0; aph ^= 1; }
-            for (int dyi = 0; dyi < ndy; ++dyi) {
-              const int tap = dyi * ndx + dxi;
+            for (int dyi = 0; dyi < ndy; dyi += TPS) {
               mbar_wait(b_empty + 8 * bs, bph ^ 1);
-              mbar_expect_tx(b_full + 8 * bs, Cfg::kBBytes);
-              tma_load_2d(b_base + bs * Cfg::kBBytes, &tmap_w, b_full + 8 * bs, c << 5,
-                          tap * p.N + n0);
+              mbar_expect_tx(b_full + 8 * bs, TPS * Cfg::kBBytes);
+#pragma unroll
+              for (int u = 0; u < TPS; ++u) {
+                const int tap = (dyi + u) * ndx + dxi;
+                tma_load_2d(b_base + (bs * TPS + u) * Cfg::kBBytes, &tmap_w, b_full + 8 * bs,
+                            c << 5, tap * p.N + n0);
+              }
               if (++bs == BS) { bs = 0; bph ^= 1; }
             }
           }
@@ -130,33 +139,47 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------ MMA issuer -----------------------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+      // Descriptors: the upper word (SBO = 1024, version, SWIZZLE_128B) is constant; the lower word
+      // is (address >> 4) | LBO, so every operand view is one 32-bit add away from the stage base.
+      // The issue loop is a single thread's dependent instruction stream: for narrow N (32-64
+      // tensor cycles per MMA) its length, not the tensor pipe, sets the pace.
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t lbo_lo = 1u << 16;
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
-      const uint32_t half_bytes = (128 >> p.tw_shift) * row_bytes;  // rows per 128-pixel half
+      const uint32_t row16 = static_cast<uint32_t>(row_bytes) >> 4;
+      const uint32_t half16 = (128u >> p.tw_shift) * row16;  // rows per 128-pixel half
       for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
         mbar_wait(acc_empty + 8 * acc, accph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * (MH * BLOCK_N);
-        uint32_t first = 1;
+        uint32_t accum = 0;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
             mbar_wait(a_full + 8 * as, aph);
-            const uint32_t a_addr = a_base + as * p.a_stage_bytes;
-            for (int dyi = 0; dyi < ndy; ++dyi) {
+            const uint32_t a_lo =
+                (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+            for (int dyi = 0; dyi < ndy; dyi += TPS) {
               mbar_wait(b_full + 8 * bs, bph);
               tc_fence_after();
-              const uint32_t b_addr = b_base + bs * Cfg::kBBytes;
+              const uint32_t b_lo =
+                  (((b_base + bs * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
-              for (int hf = 0; hf < MH; ++hf) {
-                const uint32_t a_view = a_addr + dyi * row_bytes + hf * half_bytes;
+              for (int u = 0; u < TPS; ++u) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_tf32(d0 + hf * BLOCK_N, make_smem_desc_sw128(a_view + k * 32, 16, 1024),
-                            make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
-                            (first && k == 0) ? 0u : 1u);
+                for (int hf = 0; hf < MH; ++hf) {
+                  const uint32_t av = a_lo + (dyi + u) * row16 + hf * half16;
+                  const uint32_t bv = b_lo + u * (Cfg::kBBytes >> 4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (av + 2 * k);
+                    const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (bv + 2 * k);
+                    umma_tf32(d0 + hf * BLOCK_N, adesc, bdesc, idesc,
+                              (u == 0 && k == 0) ? accum : 1u);
+                  }
                 }
+                if (u == 0) accum = 1;
               }
-              first = 0;
               umma_commit(b_empty + 8 * bs);
               if (++bs == BS) { bs = 0; bph ^= 1; }
             }
@@ -289,13 +312,17 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int MH, int AS, int BS>
+static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int block_n,
+                            int n_total) {
+  return as * a_stage_bytes + bs * tps * block_n * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
+         n_total * 4;
+}
+
+template <int BLOCK_N, int MH, int TPS>
 static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Params& p, int grid,
                    cudaStream_t stream) {
-  using Cfg = Conv2Cfg<BLOCK_N, MH, AS, BS>;
-  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, AS, BS>;
-  const int smem = AS * p.a_stage_bytes + BS * Cfg::kBBytes + 8 * Cfg::kNumBars + 32 + 1024 +
-                   p.N * 4;
+  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS>;
+  const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, BLOCK_N, p.N);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -406,20 +433,47 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
     if (int rc = encode_tmap_f32(&twm, w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
   }
   const int sms = device_sm_count();
-  const int as_n = tc.block_n >= 256 ? 2 : 3;
-  const int smem_est = as_n * p.a_stage_bytes + 4 * tc.block_n * 128 + 2048 + N * 4;
-  const int ctas_per_sm = smem_est <= 110 * 1024 ? 2 : 1;  // TMEM: <= 256 columns each
+  // ring depths: STV_CONV_STAGES="as,bs" overrides (experiments); defaults keep >= ~2000 MMA cycles
+  // of weight stages in flight (TMA latency under load) within the shared-memory budget
+  static int env_as = -1, env_bs = -1, env_tps = -1;
+  if (env_as < 0) {
+    env_as = 0; env_bs = 0; env_tps = 0;
+    if (const char* e = getenv("STV_CONV_STAGES")) sscanf(e, "%d,%d,%d", &env_as, &env_bs, &env_tps);
+  }
+  p.tps = (taps == 9 && tc.block_n <= 128) ? 3 : 1;
+  if (env_tps > 0 && taps == 9 && tc.block_n <= 128) p.tps = env_tps;
+  if (p.tps == 3) {
+    // measured (profiles/r1_stage_sweep.log): N=64 runs best as two co-resident CTAs with
+    // 2-deep rings; N=128 with a 3-deep weight ring
+    p.a_stages = 2;
+    p.b_stages = tc.block_n == 64 ? 2 : (tc.block_n == 16 ? 4 : 3);
+  } else {
+    p.a_stages = tc.block_n >= 256 ? 2 : 3;
+    p.b_stages = 4;
+  }
+  if (env_as > 0) p.a_stages = env_as;
+  if (env_bs > 0) p.b_stages = env_bs;
+  while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, tc.block_n, N) >
+             227 * 1024 && p.b_stages > 2)
+    --p.b_stages;
+  const int smem_est =
+      conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, tc.block_n, N);
+  const int ctas_per_sm = smem_est <= 113 * 1024 ? 2 : 1;  // TMEM: <= 256 columns each
   const int grid = p.tiles_total < sms * ctas_per_sm ? p.tiles_total : sms * ctas_per_sm;
 
-#define STV_L2(BN, MHV, ASV, BSV) return launch2<BN, MHV, ASV, BSV>(tx, twm, p, grid, stream)
-  if (tc.block_n == 256 && tc.mh == 2) STV_L2(256, 2, 2, 4);
-  if (tc.block_n == 256 && tc.mh == 1) STV_L2(256, 1, 2, 4);
-  if (tc.block_n == 128 && tc.mh == 2) STV_L2(128, 2, 3, 4);
-  if (tc.block_n == 128 && tc.mh == 1) STV_L2(128, 1, 3, 4);
-  if (tc.block_n == 64 && tc.mh == 2) STV_L2(64, 2, 3, 4);
-  if (tc.block_n == 64 && tc.mh == 1) STV_L2(64, 1, 3, 4);
-  if (tc.block_n == 16 && tc.mh == 2) STV_L2(16, 2, 3, 4);
-  if (tc.block_n == 16 && tc.mh == 1) STV_L2(16, 1, 3, 4);
+#define STV_L2(BN, MHV)                                                   \
+  if (tc.block_n == BN && tc.mh == MHV) {                                 \
+    if (p.tps == 3) return launch2<BN, MHV, 3>(tx, twm, p, grid, stream); \
+    return launch2<BN, MHV, 1>(tx, twm, p, grid, stream);                 \
+  }
+  if (tc.block_n == 256 && tc.mh == 2) return launch2<256, 2, 1>(tx, twm, p, grid, stream);
+  if (tc.block_n == 256 && tc.mh == 1) return launch2<256, 1, 1>(tx, twm, p, grid, stream);
+  STV_L2(128, 2)
+  STV_L2(128, 1)
+  STV_L2(64, 2)
+  STV_L2(64, 1)
+  STV_L2(16, 2)
+  STV_L2(16, 1)
 #undef STV_L2
   set_error("conv_igemm2: no kernel for N tile %d / M halves %d", tc.block_n, tc.mh);
   return 2;
