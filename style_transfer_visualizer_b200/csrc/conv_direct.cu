@@ -15,14 +15,17 @@ namespace stv {
 
 constexpr int kFirstCout = 64;
 
-// 256 threads = 64 pixels x 4 channel groups; thread cg owns channels {16*i + 4*cg + 0..3}.
-__global__ void __launch_bounds__(256)
+// One thread = 4 consecutive pixels of a row x 16 output channels (quads cq, cq+4, cq+8, cq+12 with
+// cq = lane % 4).  Each weight quad read from shared memory (one LDS.128) feeds 16 FMAs, so the
+// kernel is FMA- rather than LDS-bound, and the four cq lanes of a pixel write 64 contiguous bytes
+// (full 32-byte sectors) per store instruction.
+__global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                      const float* __restrict__ bias, int H, int W, float* __restrict__ out_pre,
-                      float* __restrict__ out_post) {
+                      const float* __restrict__ bias, int H, int W, int groups_per_row,
+                      float* __restrict__ out_pre, float* __restrict__ out_post) {
   __shared__ float4 ws[27][kFirstCout / 4];  // ws[k][c/4] = w[c..c+3][k], k = ci*9 + ky*3 + kx
   __shared__ float4 bs[kFirstCout / 4];
-  for (int i = threadIdx.x; i < 27 * kFirstCout; i += 256) {
+  for (int i = threadIdx.x; i < 27 * kFirstCout; i += 128) {
     const int c = i / 27, k = i % 27;  // torch layout [Cout][3][3][3]
     reinterpret_cast<float*>(&ws[k][c >> 2])[c & 3] = w[i];
   }
@@ -31,44 +34,63 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
   __syncthreads();
 
   const long hw = static_cast<long>(H) * W;
-  const long pix = static_cast<long>(blockIdx.x) * 64 + (threadIdx.x >> 2);
-  if (pix >= hw) return;
-  const int cg = threadIdx.x & 3;
-  const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+  const int cq = threadIdx.x & 3;
+  const long grp = static_cast<long>(blockIdx.x) * 32 + (threadIdx.x >> 2);
+  if (grp >= static_cast<long>(groups_per_row) * H) return;
+  const int y = static_cast<int>(grp / groups_per_row);
+  const int x0 = static_cast<int>(grp % groups_per_row) * 4;
 
-  float in[27];
+  float in[3][3][6];  // [channel][row][x0-1 .. x0+4]
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      const bool rok = (yy >= 0) && (yy < H);
+      const float* row = img + ci * hw + static_cast<long>(yy) * W;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = y + ky - 1, xx = x + kx - 1;
-        const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-        in[ci * 9 + ky * 3 + kx] = ok ? __ldg(img + ci * hw + static_cast<long>(yy) * W + xx) : 0.f;
+      for (int j = 0; j < 6; ++j) {
+        const int xx = x0 + j - 1;
+        in[ci][ky][j] = (rok && xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
       }
-
-  float* pre = out_pre ? out_pre + pix * kFirstCout : nullptr;
-  float* post = out_post ? out_post + pix * kFirstCout : nullptr;
-#pragma unroll
-  for (int i = 0; i < kFirstCout / 16; ++i) {
-    const int c4 = i * 4 + cg;  // float4 index of this thread's 4 channels
-    float4 acc = bs[c4];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4 wk = ws[k][c4];
-      acc.x = fmaf(in[k], wk.x, acc.x);
-      acc.y = fmaf(in[k], wk.y, acc.y);
-      acc.z = fmaf(in[k], wk.z, acc.z);
-      acc.w = fmaf(in[k], wk.w, acc.w);
     }
-    if (pre) reinterpret_cast<float4*>(pre)[c4] = acc;
-    if (post) {
-      float4 o;
-      // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
-      o.x = round_tf32(fmaxf(acc.x, 0.f)); o.y = round_tf32(fmaxf(acc.y, 0.f));
-      o.z = round_tf32(fmaxf(acc.z, 0.f)); o.w = round_tf32(fmaxf(acc.w, 0.f));
-      reinterpret_cast<float4*>(post)[c4] = o;
+
+  const long pix0 = static_cast<long>(y) * W + x0;
+#pragma unroll 1
+  for (int i = 0; i < kFirstCout / 16; ++i) {
+    const int c4 = i * 4 + cq;
+    float4 acc[4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) acc[px] = bs[c4];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 wk = ws[ci * 9 + ky * 3 + kx][c4];
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float v = in[ci][ky][px + kx];
+            acc[px].x = fmaf(v, wk.x, acc[px].x);
+            acc[px].y = fmaf(v, wk.y, acc[px].y);
+            acc[px].z = fmaf(v, wk.z, acc[px].z);
+            acc[px].w = fmaf(v, wk.w, acc[px].w);
+          }
+        }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (x0 + px < W) {
+        const long o = (pix0 + px) * (kFirstCout / 4) + c4;
+        if (out_pre) reinterpret_cast<float4*>(out_pre)[o] = acc[px];
+        if (out_post) {
+          float4 r;
+          // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
+          r.x = round_tf32(fmaxf(acc[px].x, 0.f)); r.y = round_tf32(fmaxf(acc[px].y, 0.f));
+          r.z = round_tf32(fmaxf(acc[px].z, 0.f)); r.w = round_tf32(fmaxf(acc[px].w, 0.f));
+          reinterpret_cast<float4*>(out_post)[o] = r;
+        }
+      }
     }
   }
 }
@@ -150,9 +172,11 @@ int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bi
                           int Cout, float* out_pre, float* out_post, cudaStream_t stream) {
   STV_REQUIRE(Cout == kFirstCout, "conv_first_fwd: Cout must be %d (got %d)", kFirstCout, Cout);
   STV_REQUIRE(out_pre || out_post, "conv_first_fwd: no output buffer");
-  const long hw = static_cast<long>(H) * W;
-  const unsigned blocks = static_cast<unsigned>((hw + 63) / 64);
-  conv_first_fwd_kernel<<<blocks, 256, 0, stream>>>(img_nchw, w, bias, H, W, out_pre, out_post);
+  const int groups_per_row = (W + 3) / 4;
+  const long groups = static_cast<long>(groups_per_row) * H;
+  const unsigned blocks = static_cast<unsigned>((groups + 31) / 32);
+  conv_first_fwd_kernel<<<blocks, 128, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
+                                                    out_pre, out_post);
   STV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

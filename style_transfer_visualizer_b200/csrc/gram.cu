@@ -198,14 +198,26 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const GramFinalizePa
   if (active) {
     const size_t tile_stride = static_cast<size_t>(p.pairs) * 16384;
     const float* src = p.partials + static_cast<size_t>(pair) * 16384 + m * 128 + n;
-    float r = 0.f;
-    if (p.merged) {
-      for (int s = 0; s < p.splits; ++s)
-        r += src[s * tile_stride] + src[s * tile_stride + 64 * 128 + 64];
-      if (p.x_tail) r += p.x_tail[m] * p.x_tail[n];
-    } else {
-      for (int s = 0; s < p.splits; ++s) r += src[s * tile_stride];
+    // four independent partial sums keep several loads in flight (the order is still fixed, so the
+    // result is bit-reproducible run to run)
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    const size_t off2 = p.merged ? 64 * 128 + 64 : 0;
+    int sp = 0;
+    for (; sp + 4 <= p.splits; sp += 4) {
+      const float* q = src + sp * tile_stride;
+      float a0 = q[0], a1 = q[tile_stride], a2 = q[2 * tile_stride], a3 = q[3 * tile_stride];
+      if (p.merged) {
+        a0 += q[off2]; a1 += q[tile_stride + off2];
+        a2 += q[2 * tile_stride + off2]; a3 += q[3 * tile_stride + off2];
+      }
+      r0 += a0; r1 += a1; r2 += a2; r3 += a3;
     }
+    for (; sp < p.splits; ++sp) {
+      const float* q = src + sp * tile_stride;
+      r0 += p.merged ? q[0] + q[off2] : q[0];
+    }
+    float r = (r0 + r1) + (r2 + r3);
+    if (p.merged && p.x_tail) r += p.x_tail[m] * p.x_tail[n];
     const int i = bi * 128 + m;
     const int j = bj * 128 + n;
     const float g = fminf(r, p.clamp_max) / p.n_total;
