@@ -219,6 +219,7 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
     from style_transfer_visualizer_b200.optim import FusedAdam
     from style_transfer_visualizer_b200.optimization import OptimizationRunner
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("STV_NCCL_DEBUG", "WARN")  # keep stdout to one JSON line
     info = jobs.init_distributed()
     device = torch.device("cuda", info.local_rank)
     torch.cuda.set_device(device)
@@ -314,6 +315,8 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
     e2e_value = info.world_size * e2e_steps / e2e_s
 
     if info.rank != 0:
+        jobs.barrier()  # rank 0 finishes its single-rank extras (roofline pass) first
+        jobs.shutdown()
         return
 
     # ---- roofline of the dominant kernel (tensor-core conv), measured live with CUDA events ----
@@ -369,6 +372,8 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
         "frames_read_back": Sink.count,
     }
     print(json.dumps(line), flush=True)
+    jobs.barrier()
+    jobs.shutdown()
 
 
 def main() -> None:

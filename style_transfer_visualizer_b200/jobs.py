@@ -39,8 +39,17 @@ def init_distributed(backend: str | None = None) -> RankInfo:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         be = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-        dist.init_process_group(backend=be, rank=rank, world_size=world)
+        kwargs = {}
+        if be == "nccl":
+            torch.cuda.set_device(local)
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=be, rank=rank, world_size=world, **kwargs)
     return RankInfo(rank=rank, world_size=world, local_rank=local)
+
+
+def shutdown() -> None:
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def barrier() -> None:
