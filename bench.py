@@ -260,8 +260,7 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
     sink = Sink() if wl["save_every"] else None
     runner = OptimizationRunner(model, x, make_cfg(warm + k_steps, 10), optimizer=opt,
                                 progress_bar=Bar(), video_writer=sink, use_cuda_graph=True)
-    runner._ensure_progress_bar()  # noqa: SLF001
-    runner._maybe_build_fused_step()  # noqa: SLF001
+    runner.prepare()
 
     def one_step() -> None:
         idx = runner._step_index + 1  # noqa: SLF001

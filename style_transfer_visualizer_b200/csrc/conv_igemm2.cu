@@ -75,6 +75,9 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       smem_gen + (bar_base - smem_base) + 8 * num_bars);
   // bias for all N output channels, staged once (epilogue reads it as smem broadcasts)
   float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * num_bars + 16);
+  // per-epilogue-warp 32x32 fp32 transpose tile (4 KB each), 128-byte aligned
+  const uint32_t stage_base =
+      (bar_base + 8 * num_bars + 16 + static_cast<uint32_t>(p.N) * 4 + 127u) & ~127u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,53 +233,124 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             p.out_nchw3[2 * hw + o] = __uint_as_float(r[2]);
           }
         } else {
-          const size_t row_off = (static_cast<size_t>(py) * p.W + px) * p.N + n0;
+          if (p.mask_src == nullptr && p.add_src == nullptr) {
+            // Plain forward epilogue: each lane owns one pixel row and writes its 32-channel chunk
+            // as eight 16-byte stores (the whole 128-byte line is produced back to back by one
+            // thread, which L2 merges); cheaper than the transpose when nothing has to be read.
+            const size_t row_off = (static_cast<size_t>(py) * p.W + px) * p.N + n0;
+#pragma unroll 1
+            for (int cb = 0; cb < BLOCK_N; cb += 32) {
+              uint32_t r[32];
+              tmem_ld_32x32(trow + cb, r);
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + cb + 4 * j);
+                  float4 v;
+                  v.x = fmaf(__uint_as_float(r[4 * j + 0]), alpha, b.x);
+                  v.y = fmaf(__uint_as_float(r[4 * j + 1]), alpha, b.y);
+                  v.z = fmaf(__uint_as_float(r[4 * j + 2]), alpha, b.z);
+                  v.w = fmaf(__uint_as_float(r[4 * j + 3]), alpha, b.w);
+                  const int col = cb + 4 * j;
+                  if (p.out_pre) {
+                    float4 o = v;
+                    if (p.round_pre) {
+                      o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+                      o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+                    }
+                    *reinterpret_cast<float4*>(p.out_pre + row_off + col) = o;
+                  }
+                  if (p.out_post) {
+                    float4 o;
+                    o.x = fmaxf(v.x, 0.f); o.y = fmaxf(v.y, 0.f);
+                    o.z = fmaxf(v.z, 0.f); o.w = fmaxf(v.w, 0.f);
+                    if (p.round_post) {
+                      o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+                      o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+                    }
+                    *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                  }
+                }
+              }
+            }
+            continue;
+          }
+          // TMEM gives each lane one pixel row (32 consecutive channels).  Writing that straight to
+          // global memory would touch 32 different 128-byte lines per instruction, 16 bytes each;
+          // the tile is transposed through shared memory instead so that 8 lanes cover one
+          // pixel's 128 bytes: every global load/store instruction moves 4 complete lines.
+          const uint32_t stg = stage_base + (warp - 2) * 4096;
+          const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll 1
           for (int cb = 0; cb < BLOCK_N; cb += 32) {
             uint32_t r[32];
-            tmem_ld_32x32(trow + cb, r);  // asynchronous until tmem_ld_wait()
-            // issue every global load of this 32-channel chunk before touching the results, so
-            // their latencies overlap each other and the TMEM read
-            float4 mk[8], ad[8];
-            const bool use_mask = valid && p.mask_src != nullptr;
-            const bool use_add = valid && p.add_src != nullptr;
-            if (use_mask) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                mk[j] = __ldg(reinterpret_cast<const float4*>(p.mask_src + row_off + cb) + j);
-            }
-            if (use_add) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                ad[j] = *(reinterpret_cast<const float4*>(p.add_src + row_off + cb) + j);
-            }
+            tmem_ld_32x32(trow + cb, r);
             tmem_ld_wait();
-            if (valid) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + cb + 4 * j);
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[4 * j]),
+                           "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                           : "memory");
+            }
+            __syncwarp();
+            const int col = cb + 4 * chunk;
+            const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + col);
+#pragma unroll 1
+            for (int h4 = 0; h4 < 8; h4 += 4) {  // two batches of 4 rows bound register use
+              uint32_t offs[4];
+              bool ok[4];
+              float4 mk[4], ad[4];
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int mm = hf * 128 + q * 32 + (h4 + it) * 4 + sub;
+                const int yy = ty0 + (mm >> p.tw_shift), xx = tx0 + (mm & (p.tw - 1));
+                ok[it] = (yy < p.H) && (xx < p.W);
+                offs[it] = (static_cast<uint32_t>(yy) * p.W + xx) * p.N + n0 + col;
+              }
+              if (p.mask_src) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                  if (ok[it])
+                    mk[it] = __ldg(reinterpret_cast<const float4*>(p.mask_src + offs[it]));
+              }
+              if (p.add_src) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                  if (ok[it]) ad[it] = *reinterpret_cast<const float4*>(p.add_src + offs[it]);
+              }
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rr = (h4 + it) * 4 + sub;
+                const uint32_t a = stg + rr * 128 + ((chunk ^ (rr & 7)) << 4);
+                float4 acc4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(acc4.x), "=f"(acc4.y), "=f"(acc4.z), "=f"(acc4.w)
+                             : "r"(a)
+                             : "memory");
+                if (!ok[it]) continue;
                 float4 v;
-                v.x = fmaf(__uint_as_float(r[4 * j + 0]), alpha, b.x);
-                v.y = fmaf(__uint_as_float(r[4 * j + 1]), alpha, b.y);
-                v.z = fmaf(__uint_as_float(r[4 * j + 2]), alpha, b.z);
-                v.w = fmaf(__uint_as_float(r[4 * j + 3]), alpha, b.w);
-                if (use_mask) {
-                  v.x = mk[j].x > 0.f ? v.x : 0.f;
-                  v.y = mk[j].y > 0.f ? v.y : 0.f;
-                  v.z = mk[j].z > 0.f ? v.z : 0.f;
-                  v.w = mk[j].w > 0.f ? v.w : 0.f;
+                v.x = fmaf(acc4.x, alpha, b.x);
+                v.y = fmaf(acc4.y, alpha, b.y);
+                v.z = fmaf(acc4.z, alpha, b.z);
+                v.w = fmaf(acc4.w, alpha, b.w);
+                if (p.mask_src) {
+                  v.x = mk[it].x > 0.f ? v.x : 0.f;
+                  v.y = mk[it].y > 0.f ? v.y : 0.f;
+                  v.z = mk[it].z > 0.f ? v.z : 0.f;
+                  v.w = mk[it].w > 0.f ? v.w : 0.f;
                 }
-                if (use_add) {
-                  v.x += ad[j].x; v.y += ad[j].y; v.z += ad[j].z; v.w += ad[j].w;
+                if (p.add_src) {
+                  v.x += ad[it].x; v.y += ad[it].y; v.z += ad[it].z; v.w += ad[it].w;
                 }
-                const int col = cb + 4 * j;
                 if (p.out_pre) {
                   float4 o = v;
                   if (p.round_pre) {
                     o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                     o.z = round_tf32(o.z); o.w = round_tf32(o.w);
                   }
-                  *reinterpret_cast<float4*>(p.out_pre + row_off + col) = o;
+                  *reinterpret_cast<float4*>(p.out_pre + offs[it]) = o;
                 }
                 if (p.out_post) {
                   float4 o;
@@ -286,10 +360,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                     o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                     o.z = round_tf32(o.z); o.w = round_tf32(o.w);
                   }
-                  *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                  *reinterpret_cast<float4*>(p.out_post + offs[it]) = o;
                 }
               }
             }
+            __syncwarp();  // the staging tile is rewritten by the next chunk
           }
         }
       }
@@ -315,7 +390,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int block_n,
                             int n_total) {
   return as * a_stage_bytes + bs * tps * block_n * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
-         n_total * 4;
+         n_total * 4 + 128 + 4 * 4096;  // + bias + epilogue transpose tiles
 }
 
 template <int BLOCK_N, int MH, int TPS>
@@ -403,6 +478,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   STV_REQUIRE(H > 0 && W > 0, "conv_igemm2: empty image");
   STV_REQUIRE((N == 16) == (out_nchw3 != nullptr), "conv_igemm2: N == 16 <=> NCHW3 output");
   STV_REQUIRE(out_pre || out_post || out_nchw3, "conv_igemm2: no output buffer");
+  STV_REQUIRE(static_cast<double>(H) * W * N < 4.0e9, "conv_igemm2: tensor exceeds 32-bit indexing");
 
   const TileChoice tc = choose_tiles(H, W, C, N, taps, force_n, force_mh, force_tw);
   Conv2Params p;

@@ -161,8 +161,7 @@ class OptimizationRunner:
     # ------------------------------------------------------------------ main loop
     def run(self) -> tuple[torch.Tensor, LossHistory, float]:
         """Execute all steps; returns ``(input_img, loss history, elapsed seconds)``."""
-        self._ensure_progress_bar()
-        self._maybe_build_fused_step()
+        self.prepare()
         start = time.time()
         try:
             while self._step_index < self.total_steps:
@@ -194,6 +193,17 @@ class OptimizationRunner:
         history: LossHistory = acc.export_history() if acc is not None and acc.tracks_history \
             else {}
         return self.input_img, history, elapsed
+
+    def prepare(self) -> None:
+        """One-off set-up hoisted out of the step loop: progress bar, whole-step CUDA graph and
+        the pinned frame-readback ring (pinned allocations take milliseconds)."""
+        self._ensure_progress_bar()
+        self._maybe_build_fused_step()
+        wants_frames = (self.video_writer is not None or self.gif_collector is not None) and \
+            self.config.video.save_every <= self.total_steps
+        if self._async_frames and wants_frames and self._readback is None:
+            h, w = int(self.input_img.shape[-2]), int(self.input_img.shape[-1])
+            self._readback = stv_image_io.FrameReadback(self.input_img.device, h, w)
 
     def _build_optimizer(
         self, optimizer_factory: Callable[[torch.Tensor], Optimizer] | None,
