@@ -83,6 +83,14 @@ size_t stv_gram_workspace_bytes(long hw, int C);
 int stv_gram_loss_fwd(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
                       const float* target, float clamp_max, float* gram_out, float* s_out,
                       float* loss_out, void* stream);
+/* Row-band sharding (one image split over several GPUs): the contraction of THIS GPU's pixels only,
+ * r_out [C][C] = raw F_band F_band^T (no clamp, no 1/N).  The caller all-reduces r_out over the
+ * GPUs (clamp is non-linear, so it must see the global sum) and finishes with stv_gram_from_r, where
+ * n_total = C * (pixels of the WHOLE feature map) and scratch holds C*C/256 + 1 floats. */
+int stv_gram_partial_r(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
+                       float* r_out, void* stream);
+int stv_gram_from_r(const float* r, int C, double n_total, const float* target, float clamp_max,
+                    float* gram_out, float* s_out, float* loss_out, float* scratch, void* stream);
 /* Backward of the above w.r.t. the features: dy (+)= grad_w[0] * x * S   (one GEMM instead of the
  * two that torch.mm's autograd issues).  grad_w is a DEVICE scalar (upstream dL/dloss). */
 int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* grad_w,

@@ -38,6 +38,8 @@ _SIGNATURES: dict[str, list] = {
     "stv_add_inplace": [_vp, _vp, _l, _vp],
     "stv_gram_workspace_bytes": [_l, _i],
     "stv_gram_loss_fwd": [_vp, _l, _i, _vp, _sz, _vp, _f, _vp, _vp, _vp, _vp],
+    "stv_gram_partial_r": [_vp, _l, _i, _vp, _sz, _vp, _vp],
+    "stv_gram_from_r": [_vp, _i, ctypes.c_double, _vp, _f, _vp, _vp, _vp, _vp, _vp],
     "stv_style_bwd": [_vp, _vp, _l, _i, _vp, _i, _vp, _vp],
     "stv_reduce_scratch_floats": [],
     "stv_content_loss_fwd": [_vp, _vp, _l, _vp, _vp, _vp],
@@ -107,7 +109,7 @@ def stream_ptr(device: torch.device | None = None) -> int:
 
 
 # kernels enqueued per entry point (everything else launches exactly one)
-_KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_content_loss_fwd": 2, "stv_dot": 2,
+_KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_gram_partial_r": 2, "stv_gram_from_r": 2, "stv_content_loss_fwd": 2, "stv_dot": 2,
                      "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_abi_version": 0,
                      "stv_device_check": 0}
 _launches = [0]

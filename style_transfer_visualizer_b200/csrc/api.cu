@@ -183,7 +183,17 @@ int stv_gram_loss_fwd(const float* x, long hw, int C, float* workspace, size_t w
                       const float* target, float clamp_max, float* gram_out, float* s_out,
                       float* loss_out, void* stream) {
   return gram_launch(x, hw, C, workspace, workspace_bytes, target, clamp_max, gram_out, s_out,
-                     loss_out, S(stream));
+                     loss_out, nullptr, S(stream));
+}
+int stv_gram_partial_r(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
+                       float* r_out, void* stream) {
+  return gram_launch(x, hw, C, workspace, workspace_bytes, nullptr, 0.f, nullptr, nullptr, nullptr,
+                     r_out, S(stream));
+}
+int stv_gram_from_r(const float* r, int C, double n_total, const float* target, float clamp_max,
+                    float* gram_out, float* s_out, float* loss_out, float* scratch, void* stream) {
+  return gram_from_r_launch(r, C, n_total, target, clamp_max, gram_out, s_out, loss_out, scratch,
+                            S(stream));
 }
 int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* grad_w,
                   int accumulate, float* dy, void* stream) {

@@ -183,6 +183,7 @@ struct GramFinalizeParams {
   float* gram_out;       // [C][C] or null
   float* s_out;          // [C][C] or null
   float* loss_partials;  // [gridDim.x]
+  float* raw_out;        // [C][C] raw (un-clamped, un-normalised) R; when set nothing else is written
 };
 
 __global__ void __launch_bounds__(256) gram_finalize_kernel(const GramFinalizeParams p) {
@@ -220,8 +221,12 @@ __global__ void __launch_bounds__(256) gram_finalize_kernel(const GramFinalizePa
     if (p.merged && p.x_tail) r += p.x_tail[m] * p.x_tail[n];
     const int i = bi * 128 + m;
     const int j = bj * 128 + n;
-    const float g = fminf(r, p.clamp_max) / p.n_total;
     const bool off_diag = (bi != bj);
+    if (p.raw_out) {  // row-band sharding: R partials are summed across GPUs before the clamp
+      p.raw_out[static_cast<size_t>(i) * p.C + j] = r;
+      if (off_diag) p.raw_out[static_cast<size_t>(j) * p.C + i] = r;
+    }
+    const float g = fminf(r, p.clamp_max) / p.n_total;
     if (p.gram_out) {
       p.gram_out[static_cast<size_t>(i) * p.C + j] = g;
       if (off_diag) p.gram_out[static_cast<size_t>(j) * p.C + i] = g;
@@ -294,9 +299,68 @@ size_t gram_workspace_bytes(long hw, int C) {
   return tiles + loss + 256;
 }
 
+// Epilogue of the Gram pipeline applied to an already reduced raw R (C x C, both triangles):
+// G = min(R, clamp)/N, loss partial sums and the backward seed S.  Used after the cross-GPU
+// all-reduce of R in the row-band sharded path.
+struct GramFromRParams {
+  const float* r;
+  int C;
+  float n_total, s_scale, clamp_max;
+  const float* target;
+  float* gram_out;
+  float* s_out;
+  float* loss_partials;
+};
+
+__global__ void __launch_bounds__(256) gram_from_r_kernel(const GramFromRParams p) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  float contrib = 0.f;
+  if (e < p.C * p.C) {
+    const float r = p.r[e];
+    const float g = fminf(r, p.clamp_max) / p.n_total;
+    if (p.gram_out) p.gram_out[e] = g;
+    if (p.target) {
+      const float d = g - p.target[e];
+      contrib = d * d;
+      if (p.s_out) p.s_out[e] = (r <= p.clamp_max) ? round_tf32(d * p.s_scale) : 0.f;
+    }
+  }
+  __shared__ float red[8];
+  float v = warp_sum(contrib);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    p.loss_partials[blockIdx.x] = t;
+  }
+}
+
+int gram_from_r_launch(const float* r, int C, double n_total, const float* target, float clamp_max,
+                       float* gram_out, float* s_out, float* loss_out, float* scratch,
+                       cudaStream_t stream) {
+  STV_REQUIRE(!loss_out || target, "gram_from_r: loss requested without a target");
+  GramFromRParams p;
+  p.r = r; p.C = C;
+  p.n_total = static_cast<float>(n_total);
+  p.s_scale = static_cast<float>(4.0 / (static_cast<double>(C) * C * n_total));
+  p.clamp_max = clamp_max; p.target = target; p.gram_out = gram_out; p.s_out = s_out;
+  p.loss_partials = scratch;
+  const int blocks = (C * C + 255) / 256;
+  gram_from_r_kernel<<<blocks, 256, 0, stream>>>(p);
+  STV_CHECK_CUDA(cudaGetLastError());
+  if (loss_out) {
+    gram_loss_reduce_kernel<<<1, 256, 0, stream>>>(
+        scratch, blocks, static_cast<float>(1.0 / (static_cast<double>(C) * C)), loss_out);
+    STV_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
 int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
                 const float* target, float clamp_max, float* gram_out, float* s_out,
-                float* loss_out, cudaStream_t stream) {
+                float* loss_out, float* raw_out, cudaStream_t stream) {
   STV_REQUIRE(C == 64 || (C % 128 == 0 && C <= 1024), "gram: unsupported channel count %d", C);
   STV_REQUIRE(hw >= 1, "gram: empty feature map");
   STV_REQUIRE(workspace_bytes >= gram_workspace_bytes(hw, C), "gram: workspace too small");
@@ -339,6 +403,7 @@ int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspa
   f.s_scale = static_cast<float>(4.0 / (static_cast<double>(C) * C * n_total));
   f.clamp_max = clamp_max; f.target = target; f.gram_out = gram_out; f.s_out = s_out;
   f.loss_partials = loss_partials;
+  f.raw_out = raw_out;
   const int fin_blocks = g.pairs * 64;
   gram_finalize_kernel<<<fin_blocks, 256, 0, stream>>>(f);
   STV_CHECK_CUDA(cudaGetLastError());

@@ -24,7 +24,10 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
 size_t gram_workspace_bytes(long hw, int C);
 int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,
                 const float* target, float clamp_max, float* gram_out, float* s_out,
-                float* loss_out, cudaStream_t stream);
+                float* loss_out, float* raw_out, cudaStream_t stream);
+int gram_from_r_launch(const float* r, int C, double n_total, const float* target, float clamp_max,
+                       float* gram_out, float* s_out, float* loss_out, float* scratch,
+                       cudaStream_t stream);
 
 // conv_direct.cu --------------------------------------------------------------------------
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,

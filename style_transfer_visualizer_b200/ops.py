@@ -126,6 +126,25 @@ def gram_loss_fwd(x: torch.Tensor, workspace: torch.Tensor, *, target: torch.Ten
              nat.ptr(loss_out), _s(x))
 
 
+def gram_partial_r(x: torch.Tensor, workspace: torch.Tensor, r_out: torch.Tensor) -> None:
+    """Raw ``F_band F_band^T`` of this GPU's pixels (row-band sharding); see ``stv_gram_partial_r``."""
+    _chk(x, "x")
+    c = x.shape[-1]
+    hw = x.numel() // c
+    nat.call("stv_gram_partial_r", nat.ptr(x), hw, c, nat.ptr(workspace), workspace.numel() * 4,
+             nat.ptr(r_out), _s(x))
+
+
+def gram_from_r(r: torch.Tensor, n_total: float, scratch: torch.Tensor, *,
+                target: torch.Tensor | None = None, gram_out: torch.Tensor | None = None,
+                s_out: torch.Tensor | None = None, loss_out: torch.Tensor | None = None,
+                clamp_max: float = GRAM_MATRIX_CLAMP_MAX) -> None:
+    """Clamp / normalise / loss / backward seed from an all-reduced raw R."""
+    c = r.shape[0]
+    nat.call("stv_gram_from_r", nat.ptr(r), c, float(n_total), nat.ptr(target), float(clamp_max),
+             nat.ptr(gram_out), nat.ptr(s_out), nat.ptr(loss_out), nat.ptr(scratch), _s(r))
+
+
 def style_bwd(x: torch.Tensor, s: torch.Tensor, grad_w: torch.Tensor, dy: torch.Tensor, *,
               accumulate: bool) -> None:
     c = x.shape[-1]

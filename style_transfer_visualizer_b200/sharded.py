@@ -1,0 +1,430 @@
+"""Row-band sharding of ONE large image over several GPUs (BASELINE.json configs[4]: 3840x2160).
+
+The reference runs the whole image on one device (it only warns above 3000 px, image_io.py:49-61).
+Here every rank owns a horizontal band of the image, aligned to 16 rows so that the four 2x2 pools
+never straddle a band boundary.  Per step:
+
+  * every activation / gradient buffer carries one halo row above and below its band;
+  * a 3x3 conv (or dgrad) is run over the band *including* its halo rows, which makes the band's own
+    rows exact; the two halo rows of the result are then refreshed from the neighbours with one
+    NCCL send/recv pair per direction (image-boundary halos are zeroed = the conv's zero padding);
+  * each rank contracts its own pixels into a raw Gram partial; ONE all-reduce per step sums the five
+    C x C partials (and the content-loss partial sums) over NVLink, after which clamp / 1/N / MSE /
+    backward seed are applied to the global matrices on every rank (the clamp is non-linear, so it
+    must see the global sum);
+  * the style backward uses the global seed with local features; Adam is band-local.
+
+No other collective is on the data path.  ``plan_bands`` / ``exchange_rows`` are device-agnostic
+(CPU + gloo in the tests); the engine itself needs sm_100a GPUs and NCCL.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _native as nat
+from . import ops
+from .engine import VggLossEngine
+
+BAND_ALIGN = 16  # 2^4: four pooling levels stay band-local
+
+
+def plan_bands(height: int, world_size: int, align: int = BAND_ALIGN) -> list[tuple[int, int]]:
+    """Split ``height`` rows into ``world_size`` contiguous bands whose starts are multiples of
+    ``align`` (the last band takes the unaligned remainder).  Returns [(y0, y1)] per rank."""
+    units = (height + align - 1) // align
+    if units < world_size:
+        msg = f"{height} rows are too few for {world_size} bands of {align}-aligned rows"
+        raise ValueError(msg)
+    base, extra = divmod(units, world_size)
+    bands, start = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        y0, y1 = start * align, min((start + n) * align, height)
+        bands.append((y0, y1))
+        start += n
+    return bands
+
+
+def exchange_rows(buf: torch.Tensor, rank: int, world_size: int, group=None) -> None:  # noqa: ANN001
+    """Refresh the halo rows of ``buf`` ``[B + 2, ...]`` (row 0 / row B+1) from the neighbouring
+    ranks' first / last own rows; halos on the image boundary are zeroed."""
+    rows = buf.shape[0]
+    reqs = []
+    if rank > 0:
+        reqs.append(dist.P2POp(dist.isend, buf[1], rank - 1, group))
+        reqs.append(dist.P2POp(dist.irecv, buf[0], rank - 1, group))
+    else:
+        buf[0].zero_()
+    if rank < world_size - 1:
+        reqs.append(dist.P2POp(dist.isend, buf[rows - 2], rank + 1, group))
+        reqs.append(dist.P2POp(dist.irecv, buf[rows - 1], rank + 1, group))
+    else:
+        buf[rows - 1].zero_()
+    if reqs:
+        for req in dist.batch_isend_irecv(reqs):
+            req.wait()
+
+
+@dataclass
+class _BandWorkspace:
+    band: int                       # own rows at full resolution
+    width: int
+    rows: list[int] = field(default_factory=list)       # own rows per stage
+    cols: list[int] = field(default_factory=list)
+    x_h: torch.Tensor | None = None                     # [1, 3, band + 2, W]
+    pre: list[torch.Tensor | None] = field(default_factory=list)    # haloed [rows+2, W, C]
+    post: list[torch.Tensor | None] = field(default_factory=list)
+    pool: list[torch.Tensor | None] = field(default_factory=list)
+    d_y: list[torch.Tensor | None] = field(default_factory=list)
+    d_pool: list[torch.Tensor | None] = field(default_factory=list)
+    gram_ws: list[torch.Tensor] = field(default_factory=list)
+    s_mat: list[torch.Tensor] = field(default_factory=list)
+    reduce_buf: torch.Tensor | None = None              # [sum C^2 + n_content] one all-reduce
+    losses: torch.Tensor | None = None
+    scratch: torch.Tensor | None = None
+    grad_h: torch.Tensor | None = None                  # [1, 3, band + 2, W]
+    img_send: torch.Tensor | None = None
+    img_recv: torch.Tensor | None = None
+
+
+class RowBandEngine:
+    """Forward losses / input gradient of one row band; all ranks call every method together."""
+
+    def __init__(self, layers: list[nn.Module], style_idx: list[int], content_idx: list[int],
+                 device: torch.device, group=None) -> None:  # noqa: ANN001
+        if not dist.is_initialized():
+            msg = "RowBandEngine needs an initialised torch.distributed process group"
+            raise RuntimeError(msg)
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = device
+        self.base = VggLossEngine(layers, style_idx, content_idx, device)  # stages + packed weights
+        self.stages = self.base.stages
+        self.style_idx = self.base.style_idx
+        self.content_idx = self.base.content_idx
+        conv_idx = {st.conv_idx for st in self.stages}
+        if not (set(self.style_idx) | set(self.content_idx)) <= conv_idx:
+            msg = "row-band sharding supports losses on convolution outputs only (the default taps)"
+            raise NotImplementedError(msg)
+        self._ws: dict[tuple[int, int], _BandWorkspace] = {}
+        self.style_targets: list[torch.Tensor] | None = None
+        self.content_targets: list[torch.Tensor] | None = None   # own rows, NHWC
+        self.full_hw: tuple[int, int] | None = None
+        self.band_rows: tuple[int, int] | None = None
+
+    # ------------------------------------------------------------------ helpers
+    def _xchg(self, buf: torch.Tensor) -> None:
+        exchange_rows(buf, self.rank, self.world, self.group)
+
+    def _xchg_image(self, ws: _BandWorkspace, img_h: torch.Tensor) -> None:
+        """Halo rows of the NCHW image band: the 3 planes' rows are packed into one message."""
+        b = ws.band
+        send, recv = ws.img_send, ws.img_recv
+        send[0].copy_(img_h[0, :, 1, :])
+        send[1].copy_(img_h[0, :, b, :])
+        reqs = []
+        if self.rank > 0:
+            reqs.append(dist.P2POp(dist.isend, send[0], self.rank - 1, self.group))
+            reqs.append(dist.P2POp(dist.irecv, recv[0], self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            reqs.append(dist.P2POp(dist.isend, send[1], self.rank + 1, self.group))
+            reqs.append(dist.P2POp(dist.irecv, recv[1], self.rank + 1, self.group))
+        if reqs:
+            for req in dist.batch_isend_irecv(reqs):
+                req.wait()
+        if self.rank > 0:
+            img_h[0, :, 0, :].copy_(recv[0])
+        else:
+            img_h[0, :, 0, :].zero_()
+        if self.rank < self.world - 1:
+            img_h[0, :, b + 1, :].copy_(recv[1])
+        else:
+            img_h[0, :, b + 1, :].zero_()
+
+    def _workspace(self, band: int, width: int, *, with_grad: bool) -> _BandWorkspace:
+        key = (band, width)
+        ws = self._ws.get(key)
+        dev = self.device
+
+        def buf(*shape: int) -> torch.Tensor:
+            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
+        if ws is None:
+            ws = _BandWorkspace(band=band, width=width)
+            rows, cols = band, width
+            for st in self.stages:
+                ws.rows.append(rows)
+                ws.cols.append(cols)
+                tapped = st.conv_idx in self.style_idx or st.conv_idx in self.content_idx
+                ws.pre.append(buf(rows + 2, cols, st.cout) if tapped or st.relu_idx is None
+                              else None)
+                ws.post.append(buf(rows + 2, cols, st.cout) if st.relu_idx is not None else None)
+                if st.pool_idx is not None:
+                    rows, cols = rows // 2, cols // 2
+                    ws.pool.append(buf(rows + 2, cols, st.cout))
+                else:
+                    ws.pool.append(None)
+                ws.d_y.append(None)
+                ws.d_pool.append(None)
+            total = 0
+            for idx in self.style_idx:
+                s = self._stage(idx)
+                c = self.stages[s].cout
+                ws.gram_ws.append(ops.gram_workspace(max(ws.rows[s] * ws.cols[s], 1), c, dev))
+                ws.s_mat.append(buf(c, c))
+                total += c * c
+            ws.reduce_buf = buf(total + len(self.content_idx))
+            ws.losses = buf(len(self.style_idx) + len(self.content_idx))
+            ws.scratch = buf(2 * nat.reduce_scratch_floats() + 1024)
+            ws.x_h = buf(1, 3, band + 2, width)
+            ws.img_send = buf(2, 3, width)
+            ws.img_recv = buf(2, 3, width)
+            self._ws[key] = ws
+        if with_grad and ws.grad_h is None:
+            for s, st in enumerate(self.stages):
+                ws.d_y[s] = buf(ws.rows[s] + 2, ws.cols[s], st.cout)
+                if st.pool_idx is not None:
+                    ws.d_pool[s] = buf(ws.rows[s] // 2 + 2, ws.cols[s] // 2, st.cout)
+            ws.grad_h = buf(1, 3, band + 2, width)
+        return ws
+
+    def _stage(self, conv_idx: int) -> int:
+        for s, st in enumerate(self.stages):
+            if st.conv_idx == conv_idx:
+                return s
+        raise KeyError(conv_idx)
+
+    @staticmethod
+    def _own(t: torch.Tensor) -> torch.Tensor:
+        """Own rows of a haloed NHWC buffer (contiguous view)."""
+        return t[1:t.shape[0] - 1]
+
+    def _full_rows_at(self, s: int) -> tuple[int, int]:
+        """(rows, cols) of the WHOLE feature map at stage ``s`` (global floor-mode pooling)."""
+        h, w = self.full_hw
+        for st in self.stages[:s]:
+            if st.pool_idx is not None:
+                h, w = h // 2, w // 2
+        return h, w
+
+    # ------------------------------------------------------------------ forward
+    def _run_stack(self, x_band: torch.Tensor, ws: _BandWorkspace) -> None:
+        ws.x_h[:, :, 1:-1, :].copy_(x_band)
+        self._xchg_image(ws, ws.x_h)
+        cur = None
+        n = len(self.stages)
+        for s, st in enumerate(self.stages):
+            if s == 0:
+                ops.conv3x3_first_fwd(ws.x_h, st.weight, st.bias, ws.pre[0], ws.post[0])
+            else:
+                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s])
+            cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
+            if st.pool_idx is not None:
+                ops.maxpool2_fwd(self._own(ws.post[s]), self._own(ws.pool[s]))
+                cur = ws.pool[s]
+            if s + 1 < n:
+                self._xchg(cur)  # halos for the next 3x3 conv
+
+    def _reduce_grams(self, ws: _BandWorkspace, content_sums: list[torch.Tensor]) -> list[torch.Tensor]:
+        """Raw Gram partials of the tapped layers + content partial sums -> ONE all-reduce."""
+        views, off = [], 0
+        for k, idx in enumerate(self.style_idx):
+            s = self._stage(idx)
+            c = self.stages[s].cout
+            r = ws.reduce_buf[off:off + c * c].view(c, c)
+            ops.gram_partial_r(self._own(ws.pre[s]), ws.gram_ws[k], r)
+            views.append(r)
+            off += c * c
+        for k, v in enumerate(content_sums):
+            ws.reduce_buf[off + k:off + k + 1].copy_(v)
+        dist.all_reduce(ws.reduce_buf, op=dist.ReduceOp.SUM, group=self.group)
+        return views
+
+    def compute_targets(self, style_band: torch.Tensor, content_band: torch.Tensor,
+                        style_hw: tuple[int, int], content_hw: tuple[int, int]) -> None:
+        """Targets from this rank's bands of the style / content images (full sizes given)."""
+        self.full_hw = style_hw
+        ws = self._workspace(int(style_band.shape[2]), int(style_band.shape[3]), with_grad=False)
+        self._run_stack(style_band, ws)
+        raws = self._reduce_grams(ws, [])
+        grams = []
+        for k, idx in enumerate(self.style_idx):
+            s = self._stage(idx)
+            c = self.stages[s].cout
+            fh, fw = self._full_rows_at(s)
+            g = torch.empty(c, c, device=self.device, dtype=torch.float32)
+            ops.gram_from_r(raws[k], float(c) * fh * fw, ws.scratch, gram_out=g)
+            grams.append(g)
+        self.style_targets = grams
+        self.full_hw = content_hw
+        ws = self._workspace(int(content_band.shape[2]), int(content_band.shape[3]),
+                             with_grad=False)
+        self._run_stack(content_band, ws)
+        self.content_targets = [self._own(ws.pre[self._stage(idx)]).clone()
+                                for idx in self.content_idx]
+
+    def forward_losses(self, x_band: torch.Tensor) -> torch.Tensor:
+        """Global losses (identical on every rank): style ascending, then content."""
+        if self.style_targets is None or self.content_targets is None:
+            msg = "targets must be set before computing losses."
+            raise RuntimeError(msg)
+        ws = self._workspace(int(x_band.shape[2]), int(x_band.shape[3]), with_grad=False)
+        self._run_stack(x_band.detach(), ws)
+        ns = len(self.style_idx)
+        sums = []
+        for k, idx in enumerate(self.content_idx):
+            f = self._own(ws.pre[self._stage(idx)])
+            ops.content_loss_fwd(f, self.content_targets[k], ws.scratch, ws.losses[ns + k:ns + k + 1])
+            sums.append(ws.losses[ns + k:ns + k + 1] * float(f.numel()))  # mean -> partial sum
+        raws = self._reduce_grams(ws, sums)
+        off = sum(r.numel() for r in raws)
+        for k, idx in enumerate(self.style_idx):
+            s = self._stage(idx)
+            c = self.stages[s].cout
+            fh, fw = self._full_rows_at(s)
+            ops.gram_from_r(raws[k], float(c) * fh * fw, ws.scratch, target=self.style_targets[k],
+                            s_out=ws.s_mat[k], loss_out=ws.losses[k:k + 1])
+        for k, idx in enumerate(self.content_idx):
+            s = self._stage(idx)
+            fh, fw = self._full_rows_at(s)
+            total = float(self.stages[s].cout) * fh * fw
+            ws.losses[ns + k:ns + k + 1].copy_(ws.reduce_buf[off + k:off + k + 1] / total)
+        return ws.losses
+
+    # ------------------------------------------------------------------ backward
+    def backward_losses(self, band: int, width: int, grad_w: torch.Tensor) -> torch.Tensor:
+        """d(sum_k grad_w[k] * loss_k)/d(own rows of the image): ``[1, 3, band, W]`` view."""
+        ws = self._workspace(band, width, with_grad=True)
+        grad_w = grad_w.to(torch.float32).contiguous()
+        ns = len(self.style_idx)
+        n = len(self.stages)
+        for s in range(n - 1, -1, -1):
+            st = self.stages[s]
+            down = self.stages[s + 1] if s + 1 < n else None
+            d_y = ws.d_y[s]
+            acc = False
+
+            def tap_grads(accumulate: bool) -> bool:
+                own = self._own(d_y)  # noqa: B023
+                if st.conv_idx in self.style_idx:  # noqa: B023
+                    k = self.style_idx.index(st.conv_idx)  # noqa: B023
+                    ops.style_bwd(self._own(ws.pre[s]), ws.s_mat[k], grad_w[k:k + 1], own,  # noqa: B023
+                                  accumulate=accumulate)
+                    accumulate = True
+                if st.conv_idx in self.content_idx:  # noqa: B023
+                    k = self.content_idx.index(st.conv_idx)  # noqa: B023
+                    f = self._own(ws.pre[s])  # noqa: B023
+                    fh, fw = self._full_rows_at(s)  # noqa: B023
+                    total = float(st.cout) * fh * fw  # noqa: B023
+                    # kernel scales by 2 / n_local; rescale the weight to the global element count
+                    gw = grad_w[ns + k:ns + k + 1] * (float(f.numel()) / total)
+                    ops.content_loss_bwd(f, self.content_targets[k], gw, own, accumulate=accumulate)
+                    accumulate = True
+                return accumulate
+
+            if st.pool_idx is not None:
+                ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, ws.d_pool[s])
+                ops.maxpool2_bwd(self._own(ws.d_pool[s]), self._own(ws.post[s]), self._own(d_y),
+                                 relu_mask=True)
+                tap_grads(True)
+            elif st.relu_idx is not None:
+                acc = tap_grads(False)
+                ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_src=ws.post[s],
+                                  accumulate=acc)
+            else:
+                tap_grads(False)
+            self._xchg(d_y)  # halos of the finished gradient feed the next dgrad
+        ops.conv3x3_first_dgrad_tc(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_h)
+        return ws.grad_h[:, :, 1:-1, :]
+
+
+class _BandLosses(torch.autograd.Function):
+    """Autograd bridge: forward = global losses from a band, backward = the band's gradient."""
+
+    @staticmethod
+    def forward(ctx, x_band: torch.Tensor, engine: RowBandEngine) -> torch.Tensor:  # noqa: ANN001
+        ctx.engine = engine
+        ctx.shape = (int(x_band.shape[2]), int(x_band.shape[3]))
+        return engine.forward_losses(x_band).clone()
+
+    @staticmethod
+    def backward(ctx, grad_losses: torch.Tensor):  # noqa: ANN001, ANN205
+        band, width = ctx.shape
+        grad = ctx.engine.backward_losses(band, width, grad_losses)
+        return grad.contiguous().clone(), None
+
+
+class ShardedStyleContentModel(nn.Module):
+    """``StyleContentModel`` for one image split into row bands over the ranks of a process group.
+
+    ``set_targets`` takes the FULL style / content images (every rank slices its own band);
+    ``forward`` takes this rank's band of the optimised image (``band_of``) and returns the global
+    ``(style_losses, content_losses)`` -- the same values on every rank -- so the reference-style
+    runner loop works unchanged on each rank with a band-local optimiser."""
+
+    def __init__(self, vgg_features: nn.Module, style_layers: list[int],
+                 content_layers: list[int], device: torch.device, group=None) -> None:  # noqa: ANN001
+        super().__init__()
+        from .core_model import create_feature_blocks
+
+        self.vgg_blocks, self.content_ids, self.style_ids = create_feature_blocks(
+            vgg_features, style_layers, content_layers)
+        layers: list[nn.Module] = []
+        style_idx, content_idx = [], []
+        for j, block in enumerate(self.vgg_blocks):
+            layers.extend(block.children())
+            if j in self.style_ids:
+                style_idx.append(len(layers) - 1)
+            if j in self.content_ids:
+                content_idx.append(len(layers) - 1)
+        self.engine = RowBandEngine(layers, style_idx, content_idx, device, group)
+        self.style_targets: list[torch.Tensor] | None = None
+        self.content_targets: list[torch.Tensor] | None = None
+        self.bands: list[tuple[int, int]] | None = None
+
+    def band_of(self, full_img: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of a full ``[1, 3, H, W]`` image (contiguous copy on the device)."""
+        bands = plan_bands(int(full_img.shape[2]), self.engine.world)
+        y0, y1 = bands[self.engine.rank]
+        return full_img[:, :, y0:y1, :].to(self.engine.device).contiguous()
+
+    def set_targets(self, style_img: torch.Tensor, content_img: torch.Tensor) -> None:
+        self.bands = plan_bands(int(content_img.shape[2]), self.engine.world)
+        self.engine.compute_targets(
+            self.band_of(style_img), self.band_of(content_img),
+            (int(style_img.shape[2]), int(style_img.shape[3])),
+            (int(content_img.shape[2]), int(content_img.shape[3])))
+        self.style_targets = self.engine.style_targets
+        self.content_targets = self.engine.content_targets
+
+    def forward(self, x_band: torch.Tensor):  # noqa: ANN201
+        if self.style_targets is None:
+            msg = "style_targets must be set before computing losses."
+            raise RuntimeError(msg)
+        vec = _BandLosses.apply(x_band, self.engine)
+        ns = len(self.style_ids)
+        return [vec[k] for k in range(ns)], [vec[ns + k] for k in range(len(self.content_ids))]
+
+    def gather_image(self, x_band: torch.Tensor) -> torch.Tensor | None:
+        """Assemble the full image on rank 0 (returns None elsewhere)."""
+        eng = self.engine
+        parts = [torch.empty(1, 3, y1 - y0, x_band.shape[3], device=x_band.device)
+                 for (y0, y1) in self.bands] if eng.rank == 0 else None
+        if eng.world == 1:
+            return x_band.detach().clone()
+        if eng.rank == 0:
+            parts[0].copy_(x_band.detach())
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.irecv, parts[r], r, eng.group)
+                                           for r in range(1, eng.world)])
+            for req in reqs:
+                req.wait()
+            return torch.cat(parts, dim=2)
+        for req in dist.batch_isend_irecv(
+                [dist.P2POp(dist.isend, x_band.detach().contiguous(), 0, eng.group)]):
+            req.wait()
+        return None
