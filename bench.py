@@ -107,6 +107,17 @@ def run_reference_arm(args, wl) -> None:  # noqa: ANN001
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _quiet_nccl() -> None:
+    """stdout must carry exactly one JSON line: NCCL's banner (printed at NCCL_DEBUG >= VERSION) is
+    sent to a file unless STV_NCCL_DEBUG asks for it."""
+    if "STV_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["STV_NCCL_DEBUG"]
+        return
+    os.environ.pop("NCCL_DEBUG", None)
+    os.environ["NCCL_DEBUG_FILE"] = os.path.join(tempfile.gettempdir(), "stv_nccl_%h_%p.log")
+    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -222,7 +233,7 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
     from style_transfer_visualizer_b200.optim import FusedAdam
     from style_transfer_visualizer_b200.optimization import OptimizationRunner
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("STV_NCCL_DEBUG", "WARN")  # keep stdout to one JSON line
+    _quiet_nccl()
     info = jobs.init_distributed()
     device = torch.device("cuda", info.local_rank)
     torch.cuda.set_device(device)
@@ -387,8 +398,7 @@ def run_sharded_arm(args, wl) -> None:  # noqa: ANN001
     from style_transfer_visualizer_b200.optim import FusedAdam
     from style_transfer_visualizer_b200.sharded import ShardedStyleContentModel
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("STV_NCCL_DEBUG", "WARN")
-    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+    _quiet_nccl()
     info = jobs.init_distributed()
     if info.world_size == 1 and not torch.distributed.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
