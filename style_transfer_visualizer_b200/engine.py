@@ -69,8 +69,11 @@ class VggLossEngine:
         self._workspaces: dict[tuple[int, int], _Workspace] = {}
         self.style_targets: list[torch.Tensor] | None = None          # [C, C] each
         self.content_targets_nhwc: list[torch.Tensor] | None = None   # [h, w, C] each
-        self.kernel_launches_fwd = 0
-        self.kernel_launches_bwd = 0
+        # Loss kernels (Gram, content MSE, their backward seeds) are memory-bound and independent of
+        # the next conv layers: they run on a side stream, forked/joined with events, so they
+        # overlap the tensor-core work (the fork/join structure is preserved by CUDA-graph capture).
+        self._side = torch.cuda.Stream(device=device)
+        self.overlap_losses = True
 
     # ------------------------------------------------------------------ program construction
     def _build_stages(self, layers: list[nn.Module]) -> list[_Stage]:
@@ -223,7 +226,7 @@ class VggLossEngine:
             raise ValueError(msg)
         return int(x.shape[2]), int(x.shape[3])
 
-    def _run_stack(self, x: torch.Tensor, ws: _Workspace) -> None:
+    def _run_stack(self, x: torch.Tensor, ws: _Workspace, after_stage=None) -> None:  # noqa: ANN001
         cur: torch.Tensor | None = None
         for s, st in enumerate(self.stages):
             if s == 0:
@@ -234,6 +237,12 @@ class VggLossEngine:
             if st.pool_idx is not None:
                 ops.maxpool2_fwd(ws.post[s], ws.pool[s])
                 cur = ws.pool[s]
+            if after_stage is not None:
+                after_stage(s, st)
+
+    def _stage_taps(self, st: _Stage) -> list[int]:
+        return [i for i in (st.conv_idx, st.relu_idx, st.pool_idx)
+                if i is not None and i in self._tapped]
 
     def compute_targets(self, style_img: torch.Tensor, content_img: torch.Tensor) -> None:
         """reference core_model.py:192-232 -- Grams of the style image, features of the content
@@ -264,20 +273,40 @@ class VggLossEngine:
             raise RuntimeError(msg)
         h, w = self._check_image(x)
         ws = self._workspace(h, w, with_grad=False)
-        self._run_stack(x if x.is_contiguous() else x.contiguous(), ws)
-        for k, idx in enumerate(self.style_idx):
-            t = self._tap_tensor(ws, idx)
-            ops.gram_loss_fwd(t, ws.gram_ws[k], target=self.style_targets[k], s_out=ws.s_mat[k],
-                              loss_out=ws.losses[k:k + 1])
         ns = len(self.style_idx)
-        for k, idx in enumerate(self.content_idx):
+        main = torch.cuda.current_stream(self.device)
+        side = self._side if self.overlap_losses else main
+
+        def losses_of(idx: int) -> None:
             t = self._tap_tensor(ws, idx)
-            tgt = self.content_targets_nhwc[k]
-            if tgt.shape != t.shape:
-                msg = (f"content target shape {tuple(tgt.shape)} does not match features "
-                       f"{tuple(t.shape)} at layer {idx}")
-                raise RuntimeError(msg)
-            ops.content_loss_fwd(t, tgt, ws.scratch, ws.losses[ns + k:ns + k + 1])
+            if idx in self.style_idx:
+                k = self.style_idx.index(idx)
+                ops.gram_loss_fwd(t, ws.gram_ws[k], target=self.style_targets[k],
+                                  s_out=ws.s_mat[k], loss_out=ws.losses[k:k + 1])
+            if idx in self.content_idx:
+                k = self.content_idx.index(idx)
+                tgt = self.content_targets_nhwc[k]
+                if tgt.shape != t.shape:
+                    msg = (f"content target shape {tuple(tgt.shape)} does not match features "
+                           f"{tuple(t.shape)} at layer {idx}")
+                    raise RuntimeError(msg)
+                ops.content_loss_fwd(t, tgt, ws.scratch, ws.losses[ns + k:ns + k + 1])
+
+        def after_stage(_s: int, st: _Stage) -> None:
+            taps = self._stage_taps(st)
+            if not taps:
+                return
+            if side is not main:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+            with torch.cuda.stream(side):
+                for idx in taps:
+                    losses_of(idx)
+
+        self._run_stack(x if x.is_contiguous() else x.contiguous(), ws, after_stage)
+        if side is not main:
+            main.wait_stream(side)
         ws.generation += 1
         return ws.losses, ws.generation
 
@@ -311,6 +340,23 @@ class VggLossEngine:
             raise RuntimeError(msg)
         grad_w = grad_w.to(torch.float32).contiguous()
         n = len(self.stages)
+        # Loss gradients at pre-activation taps depend only on the forward pass: issue them all up
+        # front on the side stream; the dgrad that accumulates onto one waits for its event.
+        main = torch.cuda.current_stream(self.device)
+        early: dict[int, torch.cuda.Event] = {}
+        if self.overlap_losses:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):
+                for s in range(n - 1, -1, -1):
+                    st = self.stages[s]
+                    tap_post = st.relu_idx is not None and st.relu_idx in self._tapped
+                    if st.pool_idx is None and not tap_post and st.conv_idx in self._tapped:
+                        self._tap_grads(ws, st.conv_idx, ws.pre[s], ws.d_y[s], grad_w, False)
+                        done = torch.cuda.Event()
+                        done.record(self._side)
+                        early[s] = done
         for s in range(n - 1, -1, -1):
             st = self.stages[s]
             down = self.stages[s + 1] if s + 1 < n else None
@@ -339,10 +385,16 @@ class VggLossEngine:
                     acc2 = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
                     ops.relu_bwd(d_post, ws.post[s], d_y, accumulate=acc2)
                 else:
-                    acc = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
+                    if s in early:
+                        main.wait_event(early[s])
+                        acc = True
+                    else:
+                        acc = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
                     # ReLU backward mask fused into the dgrad epilogue
                     ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_src=ws.post[s],
                                       accumulate=acc)
+            elif s in early:
+                main.wait_event(early[s])
             else:
                 self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
         ops.conv3x3_first_dgrad_tc(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_img)
