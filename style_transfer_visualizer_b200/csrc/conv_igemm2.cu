@@ -438,13 +438,13 @@ static int pick_tw(int H, int W, int mh) {
   return best;
 }
 
-static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int force_n, int force_mh,
-                               int force_tw) {
+static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_epilogue,
+                               int force_n, int force_mh, int force_tw) {
   (void)taps;
   const int sms = device_sm_count();
   int bn, mh;
   if (N == 16) { bn = 16; mh = 1; }
-  else if (N % 256 == 0) { bn = 256; mh = C >= 512 ? 2 : 1; }
+  else if (N % 256 == 0) { bn = 256; mh = (C >= 512 && !heavy_epilogue) ? 2 : 1; }
   else if (N % 128 == 0) { bn = 128; mh = 2; }
   else { bn = 64; mh = 1; }
   if (force_n <= 0 && force_mh <= 0 && N != 16) {
@@ -480,7 +480,13 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   STV_REQUIRE(out_pre || out_post || out_nchw3, "conv_igemm2: no output buffer");
   STV_REQUIRE(static_cast<double>(H) * W * N < 4.0e9, "conv_igemm2: tensor exceeds 32-bit indexing");
 
-  const TileChoice tc = choose_tiles(H, W, C, N, taps, force_n, force_mh, force_tw);
+  static int env_heavy = -1;
+  if (env_heavy < 0) {
+    const char* e = getenv("STV_CONV_HEAVY_M1");
+    env_heavy = e ? atoi(e) : 1;
+  }
+  const int heavy = env_heavy && (mask_src != nullptr || add_src != nullptr);
+  const TileChoice tc = choose_tiles(H, W, C, N, taps, heavy, force_n, force_mh, force_tw);
   Conv2Params p;
   p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps;
   p.tw = tc.tw; p.th = tc.th;
