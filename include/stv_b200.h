@@ -122,6 +122,18 @@ int stv_axpy(const float* alpha_dev, float alpha_host, const float* x, float* y,
 int stv_scale(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
               void* stream);
 
+/* Whole L-BFGS step (torch.optim.LBFGS semantics for max_iter = 1, line_search_fn = None -- the
+ * reference default, core_model.py:344-349) resident on the device: curvature-pair update,
+ * two-loop recursion in coefficient space, step-length rule, tolerance tests and x += t*d, with no
+ * host synchronisation.  hist_s / hist_y: [(history + 1)][round_up(n, 4)] floats; prev_g, d: [n];
+ * workspace: stv_lbfgs_workspace_floats(n, history) floats, ZERO-INITIALISED before the first step
+ * (it holds the iteration counters).  State words: workspace[0] = n_iter (int32),
+ * [1] = stored pairs, [3] = 1 if x was updated, [4] = 1 if the tolerance_grad early return fired. */
+size_t stv_lbfgs_workspace_floats(long n, int history);
+int stv_lbfgs_step(float* x, const float* g, long n, int history, float* hist_s, float* hist_y,
+                   float* prev_g, float* d, float* workspace, float lr, float tolerance_grad,
+                   float tolerance_change, void* stream);
+
 /* ---- timelapse frame readback (image_io.py:129-152, optimization.py:438-452) --------------- */
 /* img NCHW [3][H][W] -> out HWC uint8.  denormalize: apply ImageNet std/mean first.
  * rounding 0 = truncate (timelapse frames), 1 = round-half-even (final frame, main.py:203-214). */

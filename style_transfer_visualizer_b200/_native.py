@@ -50,6 +50,8 @@ _SIGNATURES: dict[str, list] = {
     "stv_absmax_sum": [_vp, _l, _vp, _vp, _vp],
     "stv_axpy": [_vp, _f, _vp, _vp, _l, _vp],
     "stv_scale": [_vp, _f, _vp, _vp, _l, _vp],
+    "stv_lbfgs_workspace_floats": [_l, _i],
+    "stv_lbfgs_step": [_vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp],
     "stv_frame_to_u8": [_vp, _i, _i, _i, _i, _vp, _vp],
     "stv_nchw_to_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "stv_nhwc_to_nchw": [_vp, _i, _i, _i, _vp, _vp],
@@ -60,7 +62,7 @@ _SIGNATURES: dict[str, list] = {
                            _vp],
     "stv_conv_ref": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
-_RESTYPES = {"stv_gram_workspace_bytes": _sz}
+_RESTYPES = {"stv_gram_workspace_bytes": _sz, "stv_lbfgs_workspace_floats": _sz}
 EXPORTED_SYMBOLS = ("stv_last_error", *_SIGNATURES)
 
 _lib: ctypes.CDLL | None = None
@@ -110,7 +112,7 @@ def stream_ptr(device: torch.device | None = None) -> int:
 
 # kernels enqueued per entry point (everything else launches exactly one)
 _KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_gram_partial_r": 2, "stv_gram_from_r": 2, "stv_content_loss_fwd": 2, "stv_dot": 2,
-                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_abi_version": 0,
+                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0,
                      "stv_device_check": 0}
 _launches = [0]
 

@@ -247,6 +247,14 @@ int stv_scale(const float* alpha_dev, float alpha_host, const float* x, float* y
   return scale_launch(alpha_dev, alpha_host, x, y, n, S(stream));
 }
 
+size_t stv_lbfgs_workspace_floats(long n, int history) { return lbfgs_workspace_floats(n, history); }
+int stv_lbfgs_step(float* x, const float* g, long n, int history, float* hist_s, float* hist_y,
+                   float* prev_g, float* d, float* workspace, float lr, float tolerance_grad,
+                   float tolerance_change, void* stream) {
+  return lbfgs_step_launch(x, g, n, history, hist_s, hist_y, prev_g, d, workspace, lr,
+                           tolerance_grad, tolerance_change, S(stream));
+}
+
 int stv_frame_to_u8(const float* img_nchw, int H, int W, int denormalize, int rounding,
                     unsigned char* out_hwc, void* stream) {
   return frame_to_u8_launch(img_nchw, H, W, denormalize, rounding, out_hwc, S(stream));

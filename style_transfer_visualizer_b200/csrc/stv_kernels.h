@@ -63,6 +63,11 @@ int axpy_launch(const float* alpha_dev, float alpha_host, const float* x, float*
                 cudaStream_t stream);
 int scale_launch(const float* alpha_dev, float alpha_host, const float* x, float* y, long n,
                  cudaStream_t stream);
+// lbfgs.cu
+size_t lbfgs_workspace_floats(long n, int m);
+int lbfgs_step_launch(float* x, const float* g, long n, int m, float* hist_s, float* hist_y,
+                      float* prev_g, float* d, float* workspace, float lr, float tol_grad,
+                      float tol_change, cudaStream_t stream);
 int frame_to_u8_launch(const float* img_nchw, int H, int W, int denormalize, int rounding,
                        unsigned char* out_hwc, cudaStream_t stream);
 int nchw_to_nhwc_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);

@@ -14,16 +14,20 @@ import torch
 from . import _native as nat
 from . import ops
 from .core_model import StyleContentModel
-from .optim import FusedAdam
+from .optim import FusedAdam, FusedLBFGS
 
 
 class FusedStep:
-    """Graph-captured optimisation step for (StyleContentModel, FusedAdam)."""
+    """Graph-captured optimisation step for (StyleContentModel, FusedAdam | FusedLBFGS[max_iter=1])."""
 
     @classmethod
     def try_create(cls, model: object, x: torch.Tensor, optimizer: object, style_w: float,
                    content_w: float) -> "FusedStep | None":
-        if not isinstance(model, StyleContentModel) or not isinstance(optimizer, FusedAdam):
+        if not isinstance(model, StyleContentModel):
+            return None
+        is_lbfgs = isinstance(optimizer, FusedLBFGS) and \
+            optimizer.param_groups[0]["max_iter"] == 1
+        if not isinstance(optimizer, FusedAdam) and not is_lbfgs:
             return None
         if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
             return None
@@ -34,8 +38,8 @@ class FusedStep:
             return None
         return cls(model, x, optimizer, style_w, content_w)
 
-    def __init__(self, model: StyleContentModel, x: torch.Tensor, optimizer: FusedAdam,
-                 style_w: float, content_w: float) -> None:
+    def __init__(self, model: StyleContentModel, x: torch.Tensor,
+                 optimizer: "FusedAdam | FusedLBFGS", style_w: float, content_w: float) -> None:
         self.x = x
         self.optimizer = optimizer
         self.engine = model.engine_for(x.device)
@@ -52,16 +56,20 @@ class FusedStep:
                                    device=dev, dtype=torch.float32)
         group = optimizer.param_groups[0]
         self.lr = float(group["lr"])
-        self.beta1, self.beta2 = (float(b) for b in group["betas"])
-        self.eps = float(group["eps"])
+        self.is_adam = isinstance(optimizer, FusedAdam)
         state = optimizer.state[x]
-        if not state:
-            state["step"] = 0
-            state["exp_avg"] = torch.zeros_like(x)
-            state["exp_avg_sq"] = torch.zeros_like(x)
+        if self.is_adam:
+            self.beta1, self.beta2 = (float(b) for b in group["betas"])
+            self.eps = float(group["eps"])
+            if not state:
+                state["step"] = 0
+                state["exp_avg"] = torch.zeros_like(x)
+                state["exp_avg_sq"] = torch.zeros_like(x)
+            self.adam_state = torch.zeros(3, device=dev, dtype=torch.float32)
+            self.adam_state[0] = float(state["step"])
+        else:
+            optimizer._device_state()  # noqa: SLF001  (history buffers allocated before capture)
         self.state = state
-        self.adam_state = torch.zeros(3, device=dev, dtype=torch.float32)
-        self.adam_state[0] = float(state["step"])
         self.scores = torch.zeros(3, device=dev, dtype=torch.float32)   # style, content, total
         self._tmp = torch.zeros(2, device=dev, dtype=torch.float32)
         self.height, self.width = int(x.shape[2]), int(x.shape[3])
@@ -80,9 +88,12 @@ class FusedStep:
 
     def _body(self) -> None:
         grad = self._forward_backward()
-        ops.adam_step_dev(self.x.detach(), grad, self.state["exp_avg"], self.state["exp_avg_sq"],
-                          self.adam_state, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
-                          eps=self.eps)
+        if self.is_adam:
+            ops.adam_step_dev(self.x.detach(), grad, self.state["exp_avg"],
+                              self.state["exp_avg_sq"], self.adam_state, lr=self.lr,
+                              beta1=self.beta1, beta2=self.beta2, eps=self.eps)
+        else:
+            self.optimizer.device_step(grad)
 
     def _capture(self) -> None:
         with torch.no_grad():
@@ -108,5 +119,8 @@ class FusedStep:
         if self.graph is None:
             self._capture()
         self.graph.replay()
-        self.state["step"] += 1
+        if self.is_adam:
+            self.state["step"] += 1
+        else:
+            self.state["func_evals"] = self.state.get("func_evals", 0) + 1
         return self.scores[0], self.scores[1], self.scores[2]

@@ -202,6 +202,19 @@ def scale(alpha: float | torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> None
         nat.call("stv_scale", None, float(alpha), nat.ptr(x), nat.ptr(y), x.numel(), _s(x))
 
 
+def lbfgs_workspace_floats(n: int, history: int) -> int:
+    return int(nat.load().stv_lbfgs_workspace_floats(n, history))
+
+
+def lbfgs_step(x: torch.Tensor, g: torch.Tensor, hist_s: torch.Tensor, hist_y: torch.Tensor,
+               prev_g: torch.Tensor, d: torch.Tensor, workspace: torch.Tensor, *, history: int,
+               lr: float, tolerance_grad: float, tolerance_change: float) -> None:
+    """One device-resident L-BFGS step (see ``stv_lbfgs_step``)."""
+    nat.call("stv_lbfgs_step", nat.ptr(x), nat.ptr(g), x.numel(), history, nat.ptr(hist_s),
+             nat.ptr(hist_y), nat.ptr(prev_g), nat.ptr(d), nat.ptr(workspace), lr, tolerance_grad,
+             tolerance_change, _s(x))
+
+
 def frame_to_u8(img: torch.Tensor, out: torch.Tensor, *, denormalize: bool,
                 rounding: bool = False) -> None:
     """img ``[1,3,H,W]`` fp32 -> out ``[H,W,3]`` uint8 (device)."""

@@ -76,7 +76,14 @@ class FusedAdam(Optimizer):
 
 
 class FusedLBFGS(Optimizer):
-    """L-BFGS with torch.optim.LBFGS semantics (``line_search_fn=None`` only)."""
+    """L-BFGS with torch.optim.LBFGS semantics (``line_search_fn=None`` only).
+
+    With ``max_iter == 1`` (the reference's setting) the whole update -- curvature-pair bookkeeping,
+    two-loop recursion, step-length rule, tolerance tests, ``x += t*d`` -- is ONE C-ABI call that
+    stays on the device (``stv_lbfgs_step``: three kernels, no host synchronisation), so a step costs
+    one closure evaluation plus two passes over the stored history.  ``max_iter > 1`` keeps torch's
+    host-driven control flow on the dot / axpy kernels.
+    """
 
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 1.0, max_iter: int = 20,  # noqa: PLR0913
                  max_eval: int | None = None, tolerance_grad: float = 1e-7,
@@ -94,6 +101,7 @@ class FusedLBFGS(Optimizer):
         self._image = _single_param(self)
         self._scratch: torch.Tensor | None = None
         self._scalars: torch.Tensor | None = None
+        self._dev: dict[str, torch.Tensor] | None = None   # device-resident state (max_iter == 1)
 
     # -- small device helpers ----------------------------------------------------------------
     def _bufs(self) -> tuple[torch.Tensor, torch.Tensor]:
@@ -114,9 +122,54 @@ class FusedLBFGS(Optimizer):
         host = scalars[:2].tolist()
         return host[0], host[1]
 
+    # -- device-resident single-iteration path ------------------------------------------------
+    def _device_state(self) -> dict[str, torch.Tensor]:
+        if self._dev is None:
+            x = self._image
+            n = x.numel()
+            m = int(self.param_groups[0]["history_size"])
+            stride = (n + 3) // 4 * 4
+            dev = x.device
+            self._dev = {
+                "hist_s": torch.empty(m + 1, stride, device=dev, dtype=torch.float32),
+                "hist_y": torch.empty(m + 1, stride, device=dev, dtype=torch.float32),
+                "prev_g": torch.zeros(n, device=dev, dtype=torch.float32),
+                "d": torch.zeros(n, device=dev, dtype=torch.float32),
+                "work": torch.zeros(ops.lbfgs_workspace_floats(n, m), device=dev,
+                                    dtype=torch.float32),
+            }
+        return self._dev
+
+    def device_step(self, grad: torch.Tensor) -> None:
+        """Apply one L-BFGS iteration for gradient ``grad`` entirely on the device."""
+        group = self.param_groups[0]
+        st = self._device_state()
+        ops.lbfgs_step(self._image.detach().view(-1), grad.reshape(-1), st["hist_s"], st["hist_y"],
+                       st["prev_g"], st["d"], st["work"], history=int(group["history_size"]),
+                       lr=float(group["lr"]), tolerance_grad=float(group["tolerance_grad"]),
+                       tolerance_change=float(group["tolerance_change"]))
+
+    def device_counters(self) -> dict[str, int]:
+        """n_iter / stored pairs / last-step flags (one small D2H read; for tests and logs)."""
+        if self._dev is None:
+            return {"n_iter": 0, "pairs": 0, "updated": 0, "stationary": 0}
+        w = self._dev["work"][:8].view(torch.int32).tolist()
+        return {"n_iter": w[0], "pairs": w[1], "updated": w[3], "stationary": w[4]}
+
     @torch.no_grad()
     def step(self, closure: Callable[[], torch.Tensor]):  # noqa: ANN201, C901, PLR0912, PLR0915
         group = self.param_groups[0]
+        if group["max_iter"] == 1:
+            x = self._image
+            _check_param(x)
+            with torch.enable_grad():
+                orig_loss = closure()
+            self.state[x]["func_evals"] = self.state[x].get("func_evals", 0) + 1
+            if x.grad is None:
+                msg = "closure did not produce a gradient for the image"
+                raise RuntimeError(msg)
+            self.device_step(x.grad.contiguous())
+            return orig_loss
         lr, max_iter, max_eval = group["lr"], group["max_iter"], group["max_eval"]
         tol_grad, tol_change = group["tolerance_grad"], group["tolerance_change"]
         history_size = group["history_size"]

@@ -477,7 +477,7 @@ class OptimizationRunner:
                                            self.config.optimization.content_w)
         if self._fused is None and self._use_cuda_graph:
             msg = ("use_cuda_graph=True needs this package's StyleContentModel with targets set "
-                   "and a FusedAdam optimiser on the image")
+                   "and a FusedAdam or FusedLBFGS(max_iter=1) optimiser on the image")
             raise RuntimeError(msg)
 
     def _fused_step(self, step_idx: int) -> None:
