@@ -192,3 +192,43 @@ def test_large_size_properties(cuda_device) -> None:  # noqa: ANN001
     _, gb = grad_for(0.0, 1.0, noisy)
     _, gab = grad_for(1e5, 1.0, noisy)
     assert cases.rel_l2((ga + gb).cpu().numpy(), gab.cpu().numpy()) <= 2e-3
+
+
+@pytest.mark.parametrize("n,history", [(4099, 5), (30000, 100)])
+def test_device_lbfgs_matches_torch_on_quadratic(n: int, history: int, cuda_device) -> None:  # noqa: ANN001
+    """The device-resident step (coefficient-space recursion, ring eviction, odd length) against
+    torch.optim.LBFGS on an ill-conditioned quadratic -- no TF32 anywhere, so the trajectories
+    agree to fp32 rounding for many steps."""
+    from style_transfer_visualizer_b200.optim import FusedLBFGS
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    diag = torch.logspace(-1, 1.5, n, device=cuda_device)
+    b = torch.randn(n, device=cuda_device, generator=g)
+    x0 = torch.randn(n, device=cuda_device, generator=g)
+    runs = {}
+    for kind in ("fused", "torch"):
+        x = x0.clone().requires_grad_(True)
+        opt = FusedLBFGS([x], lr=1.0, max_iter=1, max_eval=1, history_size=history) \
+            if kind == "fused" else \
+            torch.optim.LBFGS([x], lr=1.0, max_iter=1, max_eval=1, history_size=history)
+        losses = []
+
+        def closure(x=x, opt=opt, losses=losses):  # noqa: ANN001, ANN202
+            opt.zero_grad()
+            loss = 0.5 * (diag * x * x).sum() - (b * x).sum()
+            loss.backward()
+            losses.append(float(loss.detach()))
+            return loss
+
+        for _ in range(30):
+            opt.step(closure)
+        runs[kind] = (losses, x.detach().clone())
+        if kind == "fused":
+            counters = opt.device_counters()
+            assert counters["n_iter"] == 30
+            assert counters["pairs"] == min(history, 29)
+    lf, lt = np.array(runs["fused"][0]), np.array(runs["torch"][0])
+    scale = np.abs(lt).max()
+    assert np.max(np.abs(lf - lt)) / scale < 2e-4
+    assert lt[-1] < lt[0]
+    assert cases.rel_l2(runs["fused"][1].cpu().numpy(), runs["torch"][1].cpu().numpy()) < 5e-3
