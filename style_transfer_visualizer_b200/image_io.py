@@ -86,6 +86,21 @@ class FrameReadback:
         return self._host[ticket.slot].numpy().copy(), ticket.tag
 
 
+_RING_CACHE: dict[tuple[int, int, int], FrameReadback] = {}
+
+
+def shared_readback(device: torch.device, height: int, width: int) -> FrameReadback:
+    """Process-wide readback ring per (device, H, W): pinned allocations cost milliseconds to
+    hundreds of milliseconds, so consecutive jobs of the same size reuse one ring."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, height, width)
+    ring = _RING_CACHE.get(key)
+    if ring is None or ring.pending:
+        ring = FrameReadback(device, height, width)
+        _RING_CACHE[key] = ring
+    return ring
+
+
 def frame_to_numpy(img: torch.Tensor, *, normalize: bool, rounding: bool = False) -> np.ndarray:
     """One-shot synchronous variant (fused kernel + blocking copy)."""
     h, w = int(img.shape[-2]), int(img.shape[-1])

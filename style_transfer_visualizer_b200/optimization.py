@@ -203,7 +203,7 @@ class OptimizationRunner:
             self.config.video.save_every <= self.total_steps
         if self._async_frames and wants_frames and self._readback is None:
             h, w = int(self.input_img.shape[-2]), int(self.input_img.shape[-1])
-            self._readback = stv_image_io.FrameReadback(self.input_img.device, h, w)
+            self._readback = stv_image_io.shared_readback(self.input_img.device, h, w)
 
     def _build_optimizer(
         self, optimizer_factory: Callable[[torch.Tensor], Optimizer] | None,
@@ -392,7 +392,7 @@ class OptimizationRunner:
         if self._async_frames:
             if self._readback is None:
                 h, w = int(self.input_img.shape[-2]), int(self.input_img.shape[-1])
-                self._readback = stv_image_io.FrameReadback(self.input_img.device, h, w)
+                self._readback = stv_image_io.shared_readback(self.input_img.device, h, w)
             # hand over the previous frame (its copy finished long ago), then queue this one
             while self._readback.pending >= self._readback.depth - 1:
                 self._deliver_frame(*self._readback.collect())

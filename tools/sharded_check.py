@@ -33,6 +33,8 @@ def main() -> int:
     if "--big" in sys.argv:
         sizes = [(1080, 1920, 1080, 1920)]
     for (h, w, sh, sw) in sizes:
+        if min(h, sh) < 16 * info.world_size:
+            continue  # fewer 16-row units than ranks
         feats = synthetic.random_vgg19_features(0)
         content = synthetic.synthetic_image(1, h, w)
         style = synthetic.synthetic_image(2, sh, sw)
