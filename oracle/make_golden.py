@@ -49,6 +49,8 @@ CASES: dict[str, dict] = {
                             style_w=1e9),
     "lbfgs_content_64": dict(h=64, w=64, opt="lbfgs", lr=1.0, steps=6, init="content",
                              style_w=1e10),
+    # BASELINE.json configs[1] at full size (first 8 of its 300 steps; the CPU needs ~1 s per step)
+    "adam_content_512_c2": dict(h=512, w=512, opt="adam", lr=0.01, steps=8, init="content"),
     # BASELINE.json configs[0]: 256x256, Adam, 50 steps, content init, on CPU
     "adam_content_256_c1": dict(h=256, w=256, opt="adam", lr=0.01, steps=50, init="content",
                                 save_every=25, csv=True),

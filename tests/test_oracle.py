@@ -15,7 +15,7 @@ from oracle import reference_shim
 from oracle import stv_oracle as orc
 from tests import _cases as cases
 
-FAST = [n for n in cases.golden_names() if "256" not in n]
+FAST = [n for n in cases.golden_names() if "256" not in n and "512" not in n]
 
 
 def _run_oracle(cfg: dict):  # noqa: ANN202
@@ -63,6 +63,14 @@ def test_oracle_matches_reference_golden_c1_256() -> None:
     _model, res = _run_oracle(cfg)
     _check(cfg, gold, res, rtol=2e-3)
     assert res.content[0] == 0.0  # content init => exactly zero content loss at step 1
+
+
+@pytest.mark.slow
+def test_oracle_matches_reference_golden_c2_512() -> None:
+    """BASELINE.json configs[1] at full size (first 8 steps)."""
+    cfg, gold = cases.load_golden("adam_content_512_c2")
+    _model, res = _run_oracle(cfg)
+    _check(cfg, gold, res, rtol=2e-3)
 
 
 def test_gram_properties() -> None:
