@@ -106,6 +106,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch, bias staging -- none of it touches activations) may overlap the tail of the previous
+  // kernel in the stream; from here on we read / write tensors it may still be using.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------ TMA producer --------------------------------------------
@@ -405,8 +410,22 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
                                         227 * 1024));
     attr_smem = 227 * 1024;
   }
-  kern<<<grid, kThreads2, smem, stream>>>(tx, tw, p);
-  STV_CHECK_CUDA(cudaGetLastError());
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("STV_PDL");
+    use_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  STV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, p));
   return 0;
 }
 
