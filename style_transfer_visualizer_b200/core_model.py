@@ -121,8 +121,21 @@ def initialize_input(content_img: torch.Tensor, method: InitMethod) -> torch.Ten
 
 
 def initialize_vgg() -> nn.Module:
-    """Pretrained, frozen, eval-mode ``vgg19().features`` (reference core_model.py:103-117)."""
+    """Pretrained, frozen, eval-mode ``vgg19().features`` (reference core_model.py:103-117).
+
+    Offline machines (no weight download possible) can set ``STV_RANDOM_VGG_SEED=<int>`` to get the
+    seeded random-init network the benchmarks and tests use; a warning is logged."""
+    import os
+
     from torchvision.models import VGG19_Weights, vgg19
+
+    seed = os.environ.get("STV_RANDOM_VGG_SEED")
+    if seed is not None:
+        from .synthetic import random_vgg19_features
+
+        logger.warning("STV_RANDOM_VGG_SEED=%s: using RANDOM-INIT VGG19 weights (not pretrained)",
+                       seed)
+        return random_vgg19_features(int(seed))
 
     weights = VGG19_Weights.IMAGENET1K_V1
     cache = Path(torch.hub.get_dir()) / "checkpoints" / Path(urlparse(weights.url).path).name

@@ -232,3 +232,48 @@ def test_device_lbfgs_matches_torch_on_quadratic(n: int, history: int, cuda_devi
     assert np.max(np.abs(lf - lt)) / scale < 2e-4
     assert lt[-1] < lt[0]
     assert cases.rel_l2(runs["fused"][1].cpu().numpy(), runs["torch"][1].cpu().numpy()) < 5e-3
+
+
+def test_cli_end_to_end_offline(cuda_device, tmp_path, monkeypatch) -> None:  # noqa: ANN001
+    """The reference's e2e CLI smoke (tests/test_cli.py:852-897: 64x64, 2 steps, --final-only,
+    white init) through this package's CLI, with the offline random-weight switch, default
+    optimiser (L-BFGS) and a TOML config + flag override."""
+    from PIL import Image
+
+    from style_transfer_visualizer_b200 import cli
+
+    rng = np.random.default_rng(0)
+    for name in ("content.png", "style.png"):
+        Image.fromarray(rng.integers(0, 255, (64, 80, 3), dtype=np.uint8)).save(tmp_path / name)
+    toml = tmp_path / "config.toml"
+    toml.write_text("[optimization]\nsteps = 5\ninit_method = \"white\"\n[output]\nlog_every = 1\n")
+    monkeypatch.setenv("STV_RANDOM_VGG_SEED", "0")
+    out_dir = tmp_path / "out"
+    rc = cli.main(["--content", str(tmp_path / "content.png"), "--style", str(tmp_path / "style.png"),
+                   "--config", str(toml), "--steps", "2", "--final-only", "--output", str(out_dir),
+                   "--log-loss", str(tmp_path / "loss.csv"), "--device", "cuda"])
+    assert rc == 0
+    png = out_dir / "stylized_content_x_style.png"
+    assert png.exists()
+    img = np.asarray(Image.open(png))
+    assert img.shape == (64, 80, 3) and img.dtype == np.uint8
+    rows = (tmp_path / "loss.csv").read_text().strip().splitlines()
+    assert rows[0] == "step,style_loss,content_loss,total_loss" and len(rows) == 3
+
+
+def test_1080p_step_properties(cuda_device) -> None:  # noqa: ANN001
+    """BASELINE configs[2] size (1920x1080, odd pooled sizes 135 -> 67): content init gives exactly
+    zero content loss, two evaluations are bit-identical, losses are finite and positive."""
+    cfg = {"h": 1080, "w": 1920, "init": "content", "weight_seed": 0,
+           "style_layers": [0, 5, 10, 19, 28], "content_layers": [21]}
+    model, x0 = _gpu_run.build_model(cfg, cuda_device)
+    outs = []
+    for _ in range(2):
+        x = x0.clone().requires_grad_(True)
+        sl, cl = model(x)
+        (1e5 * torch.stack(sl).sum() + torch.stack(cl).sum()).backward()
+        outs.append(([float(v.detach()) for v in sl + cl], x.grad.clone()))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][0][-1] == 0.0
+    assert all(v > 0 and np.isfinite(v) for v in outs[0][0][:-1])
+    assert bool(torch.isfinite(outs[0][1]).all())
