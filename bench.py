@@ -424,22 +424,29 @@ def run_sharded_arm(args, wl) -> None:  # noqa: ANN001
     content = synthetic.synthetic_image(1, h, w)
     style = synthetic.synthetic_image(2, h, w)
     model.set_targets(style, content)
-    x = model.band_of(content).requires_grad_(True)
-    opt = FusedAdam([x], lr=LR)
+    from style_transfer_visualizer_b200.sharded import ShardedFusedStep
+
+    x = model.band_of(content)
+    fused = ShardedFusedStep(model, x, lr=LR, style_w=STYLE_W, content_w=CONTENT_W)
     last = []
+    del FusedAdam
 
-    def closure():
-        opt.zero_grad()
-        sl, cl = model(x)
-        total = STYLE_W * torch.stack(sl).sum() + CONTENT_W * torch.stack(cl).sum()
-        total.backward()
-        last[:] = [total.detach()]
-        return total
+    class _Opt:
+        @staticmethod
+        def step(_closure):  # noqa: ANN001, ANN205
+            last[:] = [fused.step()]
 
+    opt, closure = _Opt, None
     launches0 = nat.launch_count()
     for _ in range(warm):
         opt.step(closure)
     per_step = (nat.launch_count() - launches0) // warm
+    graph_mode = "eager"
+    if args.sharded_graph:
+        fused.capture()
+        graph_mode = "cuda-graph (NCCL send/recv + all-reduce captured)"
+        for _ in range(2):
+            opt.step(closure)
     torch.cuda.synchronize(device)
     jobs.barrier()
     sampler = ClockSampler(info.local_rank) if info.rank == 0 else None
@@ -466,14 +473,25 @@ def run_sharded_arm(args, wl) -> None:  # noqa: ANN001
             "config": {"workload": wl["name"], "height": h, "width": w, "optimizer": "adam",
                        "parallelism": f"row bands x{info.world_size} (16-row aligned), 1 halo row "
                                       "send/recv per conv, one Gram all-reduce per step",
-                       "l2": "no flush: working set far above the 126 MB L2"},
+                       "l2": "no flush: working set far above the 126 MB L2",
+                       "step_launch": graph_mode},
             "e2e": None, "gpu_launches": per_step * k_steps, "gpu_launches_per_step": per_step,
             "clocks": clocks, "final_loss": loss,
             "whole_job_tflops": flops / (ms_total / k_steps / 1e3) / 1e12,
         }
         print(json.dumps(line), flush=True)
+    # Tear-down: drop the captured graph before the communicator goes away, and leave without
+    # destroy_process_group() -- destroying an NCCL communicator that was used inside a captured
+    # graph blocked at exit on this stack (torch 2.11 / NCCL 2.28).
+    torch.cuda.synchronize(device)
+    fused.graph = None
+    import gc
+
+    gc.collect()
     jobs.barrier()
-    jobs.shutdown()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main() -> None:
@@ -484,6 +502,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-graph", type=int, default=1,
+                    help="4k workload: replay the sharded step from a CUDA graph (0 = eager)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.steps is None:

@@ -428,3 +428,63 @@ class ShardedStyleContentModel(nn.Module):
                 [dist.P2POp(dist.isend, x_band.detach().contiguous(), 0, eng.group)]):
             req.wait()
         return None
+
+
+class ShardedFusedStep:
+    """Whole sharded Adam step (forward with halo exchanges, the Gram all-reduce, backward, update)
+    captured into one CUDA graph per rank.  NCCL send/recv and all-reduce are captured like any
+    other stream work, so a replay costs one launch instead of ~75 kernel launches plus ~27 NCCL
+    group calls issued from Python -- at 8 GPUs the eager step is bound by that host work."""
+
+    def __init__(self, model: ShardedStyleContentModel, x_band: torch.Tensor, *, lr: float,
+                 style_w: float, content_w: float, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8) -> None:
+        self.engine = model.engine
+        self.x = x_band
+        dev = x_band.device
+        ns, nc = len(self.engine.style_idx), len(self.engine.content_idx)
+        self.ns = ns
+        self.style_w, self.content_w = float(style_w), float(content_w)
+        self.grad_w = torch.tensor([self.style_w] * ns + [self.content_w] * nc, device=dev)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.m = torch.zeros_like(x_band)
+        self.v = torch.zeros_like(x_band)
+        self.adam_state = torch.zeros(3, device=dev)
+        self.grad = torch.zeros_like(x_band)
+        self.scores = torch.zeros(3, device=dev)
+        self._tmp = torch.zeros(2, device=dev)
+        self.graph: torch.cuda.CUDAGraph | None = None
+
+    def _body(self) -> None:
+        eng = self.engine
+        band, width = int(self.x.shape[2]), int(self.x.shape[3])
+        losses = eng.forward_losses(self.x.detach())
+        torch.sum(losses[:self.ns], dim=0, out=self.scores[0])
+        torch.sum(losses[self.ns:], dim=0, out=self.scores[1])
+        torch.mul(self.scores[0], self.style_w, out=self._tmp[0])
+        torch.mul(self.scores[1], self.content_w, out=self._tmp[1])
+        torch.add(self._tmp[0], self._tmp[1], out=self.scores[2])
+        self.grad.copy_(eng.backward_losses(band, width, self.grad_w))
+        ops.adam_step_dev(self.x.detach(), self.grad, self.m, self.v, self.adam_state, lr=self.lr,
+                          beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+
+    def eager_step(self) -> torch.Tensor:
+        with torch.no_grad():
+            self._body()
+        return self.scores[2]
+
+    def capture(self) -> None:
+        """All ranks must call this together (the captured NCCL calls are collective)."""
+        with torch.no_grad():
+            dev = self.x.device
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._body()
+            self.graph = graph
+
+    def step(self) -> torch.Tensor:
+        if self.graph is None:
+            return self.eager_step()
+        self.graph.replay()
+        return self.scores[2]
