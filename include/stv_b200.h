@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define STV_ABI_VERSION 1
+#define STV_ABI_VERSION 2
 
 const char* stv_last_error(void);
 int stv_abi_version(void);
@@ -44,11 +44,14 @@ int stv_pack_conv_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout
  * either may be NULL. */
 int stv_conv3x3_first_fwd(const float* img_nchw, const float* w /*[64][3][3][3]*/,
                           const float* bias, int H, int W, int Cout, float* out_pre,
-                          float* out_post, void* stream);
+                          float* out_post, int round_pre, void* stream);
 /* 3x3 pad-1 conv on the tensor cores (tcgen05, TF32 multiply, FP32 accumulate).
- * x: NHWC [H][W][Cin], w_fwd from stv_pack_conv_weights, Cin % 32 == 0, Cout % 64 == 0. */
+ * x: NHWC [H][W][Cin], w_fwd from stv_pack_conv_weights, Cin % 32 == 0, Cout % 64 == 0.
+ * out_post is always stored rounded to TF32 (it is the next conv's MMA operand); round_pre != 0
+ * stores out_pre rounded as well -- used when out_pre only feeds the Gram contraction, whose MMA
+ * would otherwise truncate it (a systematic shrink of the Gram entries). */
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
-                    int Cout, float* out_pre, float* out_post, void* stream);
+                    int Cout, float* out_pre, float* out_post, int round_pre, void* stream);
 
 /* ---- VGG conv stack: input gradient (autograd of the above; optimization.py:313) ---------- */
 /* dx = [relu_src > 0] .* conv_transpose(dy) (+ dx when accumulate != 0).

@@ -120,18 +120,20 @@ int stv_pack_conv_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout
 }
 
 int stv_conv3x3_first_fwd(const float* img_nchw, const float* w, const float* bias, int H, int W,
-                          int Cout, float* out_pre, float* out_post, void* stream) {
-  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, S(stream));
+                          int Cout, float* out_pre, float* out_post, int round_pre, void* stream) {
+  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, round_pre,
+                               S(stream));
 }
 
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
-                    int Cout, float* out_pre, float* out_post, void* stream) {
+                    int Cout, float* out_pre, float* out_post, int round_pre, void* stream) {
+  const int rf = 2 | (round_pre ? 1 : 0);
   // out_post feeds the next conv's MMA -> stored tf32-rounded; out_pre (read by the losses) exact.
   if (use_conv_v1())
     return conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr,
-                             out_pre, out_post, 2, 0, 0, 0, S(stream));
+                             out_pre, out_post, rf, 0, 0, 0, S(stream));
   return conv_igemm2_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
-                            out_post, 2, nullptr, 0, 0, 0, S(stream));
+                            out_post, rf, nullptr, 0, 0, 0, S(stream));
 }
 
 int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,

@@ -22,7 +22,7 @@ constexpr int kFirstCout = 64;
 __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                       const float* __restrict__ bias, int H, int W, int groups_per_row,
-                      float* __restrict__ out_pre, float* __restrict__ out_post) {
+                      int round_pre, float* __restrict__ out_pre, float* __restrict__ out_post) {
   __shared__ float4 ws[27][kFirstCout / 4];  // ws[k][c/4] = w[c..c+3][k], k = ci*9 + ky*3 + kx
   __shared__ float4 bs[kFirstCout / 4];
   for (int i = threadIdx.x; i < 27 * kFirstCout; i += 128) {
@@ -82,7 +82,13 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
     for (int px = 0; px < 4; ++px) {
       if (x0 + px < W) {
         const long o = (pix0 + px) * (kFirstCout / 4) + c4;
-        if (out_pre) reinterpret_cast<float4*>(out_pre)[o] = acc[px];
+        if (out_pre) {
+          float4 r = acc[px];
+          if (round_pre) {  // pre only feeds the Gram MMA: store it tf32-rounded
+            r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
+          }
+          reinterpret_cast<float4*>(out_pre)[o] = r;
+        }
         if (out_post) {
           float4 r;
           // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
@@ -169,14 +175,15 @@ __global__ void conv_ref_kernel(const float* __restrict__ x, const float* __rest
 }
 
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
-                          int Cout, float* out_pre, float* out_post, cudaStream_t stream) {
+                          int Cout, float* out_pre, float* out_post, int round_pre,
+                          cudaStream_t stream) {
   STV_REQUIRE(Cout == kFirstCout, "conv_first_fwd: Cout must be %d (got %d)", kFirstCout, Cout);
   STV_REQUIRE(out_pre || out_post, "conv_first_fwd: no output buffer");
   const int groups_per_row = (W + 3) / 4;
   const long groups = static_cast<long>(groups_per_row) * H;
   const unsigned blocks = static_cast<unsigned>((groups + 31) / 32);
   conv_first_fwd_kernel<<<blocks, 128, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
-                                                    out_pre, out_post);
+                                                    round_pre, out_pre, out_post);
   STV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,7 +31,8 @@ int gram_from_r_launch(const float* r, int C, double n_total, const float* targe
 
 // conv_direct.cu --------------------------------------------------------------------------
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
-                          int Cout, float* out_pre, float* out_post, cudaStream_t stream);
+                          int Cout, float* out_pre, float* out_post, int round_pre,
+                          cudaStream_t stream);
 int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
                             float* dimg_nchw, cudaStream_t stream);
 int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,

@@ -230,15 +230,23 @@ class VggLossEngine:
         cur: torch.Tensor | None = None
         for s, st in enumerate(self.stages):
             if s == 0:
-                ops.conv3x3_first_fwd(x, st.weight, st.bias, ws.pre[0], ws.post[0])
+                ops.conv3x3_first_fwd(x, st.weight, st.bias, ws.pre[0], ws.post[0],
+                                      round_pre=self._round_pre(st))
             else:
-                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s])
+                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s],
+                                round_pre=self._round_pre(st))
             cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
             if st.pool_idx is not None:
                 ops.maxpool2_fwd(ws.post[s], ws.pool[s])
                 cur = ws.pool[s]
             if after_stage is not None:
                 after_stage(s, st)
+
+    def _round_pre(self, st: _Stage) -> bool:
+        """A conv output tapped by style losses only is consumed solely by tensor-core kernels
+        (Gram, Gram backward): store it tf32-rounded so their operand truncation is exact.  Content
+        taps keep the exact fp32 value (the content MSE is fp32 arithmetic)."""
+        return st.conv_idx in self.style_idx and st.conv_idx not in self.content_idx
 
     def _stage_taps(self, st: _Stage) -> list[int]:
         return [i for i in (st.conv_idx, st.relu_idx, st.pool_idx)

@@ -34,20 +34,22 @@ def pack_conv_weights(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
 
 
 def conv3x3_first_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
-                      out_pre: torch.Tensor | None, out_post: torch.Tensor | None) -> None:
+                      out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
+                      round_pre: bool = False) -> None:
     _chk(img, "img")
     h, wd = img.shape[-2], img.shape[-1]
     nat.call("stv_conv3x3_first_fwd", nat.ptr(img), nat.ptr(w), nat.ptr(bias), h, wd, w.shape[0],
-             nat.ptr(out_pre), nat.ptr(out_post), _s(img))
+             nat.ptr(out_pre), nat.ptr(out_post), int(round_pre), _s(img))
 
 
 def conv3x3_fwd(x: torch.Tensor, w_fwd: torch.Tensor, bias: torch.Tensor | None,
-                out_pre: torch.Tensor | None, out_post: torch.Tensor | None) -> None:
+                out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
+                round_pre: bool = False) -> None:
     _chk(x, "x")
     h, wd, cin = x.shape
     cout = w_fwd.shape[1]
     nat.call("stv_conv3x3_fwd", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
-             nat.ptr(out_pre), nat.ptr(out_post), _s(x))
+             nat.ptr(out_pre), nat.ptr(out_post), int(round_pre), _s(x))
 
 
 def conv3x3_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, dx: torch.Tensor,

@@ -193,6 +193,9 @@ class RowBandEngine:
             ws.grad_h = buf(1, 3, band + 2, width)
         return ws
 
+    def _round_pre(self, st) -> bool:  # noqa: ANN001
+        return self.base._round_pre(st)  # noqa: SLF001
+
     def _stage(self, conv_idx: int) -> int:
         for s, st in enumerate(self.stages):
             if st.conv_idx == conv_idx:
@@ -220,9 +223,11 @@ class RowBandEngine:
         n = len(self.stages)
         for s, st in enumerate(self.stages):
             if s == 0:
-                ops.conv3x3_first_fwd(ws.x_h, st.weight, st.bias, ws.pre[0], ws.post[0])
+                ops.conv3x3_first_fwd(ws.x_h, st.weight, st.bias, ws.pre[0], ws.post[0],
+                                      round_pre=self._round_pre(st))
             else:
-                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s])
+                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s],
+                                round_pre=self._round_pre(st))
             cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
             if st.pool_idx is not None:
                 ops.maxpool2_fwd(self._own(ws.post[s]), self._own(ws.pool[s]))

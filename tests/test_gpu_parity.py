@@ -9,9 +9,11 @@ optimisers (which call the C-ABI kernels), eagerly and through the whole-step CU
 Stated tolerance (TF32 multiply / FP32 accumulate in the convolutions, the Gram contraction and the
 style backward; everything else fp32) -- the reference itself runs its convolutions in TF32 on
 CUDA (torch.backends.cudnn.allow_tf32 defaults to True):
-    per-layer style loss      relative 1e-2
+    per-layer style loss      relative 5e-3  (measured <= 1.1e-3; stock torch on CUDA: <= 1.0e-3)
     per-layer content loss    absolute 1e-4 x total loss   (exactly 0 for content init)
-    input gradient            relative L2 5e-2 and cosine >= 0.999
+    input gradient            relative L2 5e-2 and cosine >= 0.999  (measured <= 1.5e-2; stock
+                              torch on CUDA with cuDNN TF32 convs: <= 1.4e-2, profiles/
+                              r1_parity_vs_torch_cuda.log)
     Adam loss trajectory      relative 3e-2 at every step
     Adam final image          relative L2 5e-2
     timelapse frames          <= 4 LSB, <= 20 % of bytes differing
@@ -36,7 +38,7 @@ LBFGS_CASES = [n for n in cases.golden_names() if n.startswith("lbfgs")]
 
 
 def _check_first_closure(m: dict[str, float]) -> None:
-    assert m["layer_style_rel_max"] <= 1e-2
+    assert m["layer_style_rel_max"] <= 5e-3
     assert m["layer_content_abs_over_total"] <= 1e-4
     assert m["grad_rel_l2"] <= 5e-2
     assert m["grad_cosine"] >= 0.999
