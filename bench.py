@@ -31,6 +31,9 @@ WORKLOADS = {
     "1080p": dict(h=1080, w=1920, save_every=10, steps=100,
                   name="configs[2]: VGG19 1920x1080, Adam, save_every=10 frame readback, "
                        "content init, random-init weights, synthetic images"),
+    "jobs64": dict(h=512, w=512, save_every=0, steps=30,
+                   name="configs[3]: 64 independent 512x512 content/style pairs, Adam, "
+                        "statically partitioned over the GPUs (no collective)"),
     "4k": dict(h=2160, w=3840, save_every=0, steps=20,
                name="configs[4]: VGG19 3840x2160 single image, Adam, row-band sharded conv stack "
                     "with halo exchange + Gram all-reduce over the GPUs"),
@@ -399,6 +402,63 @@ def run_gpu_arm(args, wl) -> None:  # noqa: ANN001, PLR0915
     jobs.shutdown()
 
 
+def run_jobs_arm(args, wl) -> None:  # noqa: ANN001
+    """configs[3]: 64 independent jobs; every rank runs its static share through StyleJobRunner
+    (model, workspaces, pinned buffers and the captured step graph reused across jobs).  The timed
+    region is end to end per job: pinned host images in, result image out."""
+    import torch
+
+    import style_transfer_visualizer_b200.core_model as cm
+    from style_transfer_visualizer_b200 import _native as nat
+    from style_transfer_visualizer_b200 import jobs, synthetic
+
+    _quiet_nccl()
+    info = jobs.init_distributed()
+    device = torch.device("cuda", info.local_rank)
+    torch.cuda.set_device(device)
+    nat.require_device(device)
+    n_jobs, steps = 64, args.steps
+    mine = jobs.partition_jobs(n_jobs, info.world_size, info.rank)
+    original = cm.initialize_vgg
+    cm.initialize_vgg = lambda: synthetic.random_vgg19_features(0)
+    try:
+        model = cm.StyleContentModel([0, 5, 10, 19, 28], [21])
+    finally:
+        cm.initialize_vgg = original
+    runner = jobs.StyleJobRunner(model, wl["h"], wl["w"], steps=steps, lr=LR, style_w=STYLE_W,
+                                 content_w=CONTENT_W, device=device)
+    pairs = [(synthetic.synthetic_image(1 + 2 * j, wl["h"], wl["w"]),
+              synthetic.synthetic_image(2 + 2 * j, wl["h"], wl["w"])) for j in mine]
+    runner.run_job(*pairs[0])  # warm-up job: workspace allocation + graph capture
+    torch.cuda.synchronize(device)
+    jobs.barrier()
+    t0 = time.perf_counter()
+    losses = [runner.run_job(c, s)[1] for c, s in pairs]
+    torch.cuda.synchronize(device)
+    local = time.perf_counter() - t0
+    jobs.barrier()
+    total_s = jobs.max_over_ranks(local, device)
+    if info.rank == 0:
+        line = {
+            "metric": METRIC, "value": n_jobs * steps / total_s, "unit": "steps/s",
+            "n_gpus": info.world_size, "steps": steps, "warmup": 1,
+            "ms_per_step": total_s / (len(mine) * steps) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": wl["name"], "jobs": n_jobs, "jobs_per_gpu": len(mine),
+                       "steps_per_job": steps, "height": wl["h"], "width": wl["w"],
+                       "timing": "host wall clock per rank over its jobs (H2D of both images and "
+                                 "D2H of the result inside), max over ranks"},
+            "jobs_per_second": n_jobs / total_s,
+            "e2e": {"value": n_jobs * steps / total_s, "unit": "steps/s",
+                    "h2d_bytes_per_step": 2 * 3 * wl["h"] * wl["w"] * 4 / steps,
+                    "d2h_bytes_per_step": 3 * wl["h"] * wl["w"] * 4 / steps},
+            "final_loss_first_job": losses[0],
+        }
+        print(json.dumps(line), flush=True)
+    jobs.barrier()
+    jobs.shutdown()
+
+
 def run_sharded_arm(args, wl) -> None:  # noqa: ANN001
     """configs[4]: ONE image split into row bands over all ranks (strong scaling)."""
     import torch
@@ -512,6 +572,8 @@ def main() -> None:
         run_reference_arm(args, wl)
     elif args.workload == "4k":
         run_sharded_arm(args, wl)
+    elif args.workload == "jobs64":
+        run_jobs_arm(args, wl)
     else:
         run_gpu_arm(args, wl)
 

@@ -259,17 +259,30 @@ class VggLossEngine:
         ch, cw = self._check_image(content_img)
         ws = self._workspace(sh, sw, with_grad=False)
         self._run_stack(style_img.contiguous(), ws)
+        # Existing target tensors of matching shape are overwritten IN PLACE, so a captured step
+        # graph (which holds their addresses) stays valid when the next job's targets are loaded.
+        old_grams = self.style_targets or []
         grams = []
         for k, idx in enumerate(self.style_idx):
             t = self._tap_tensor(ws, idx)
-            g = torch.empty(t.shape[-1], t.shape[-1], device=self.device, dtype=torch.float32)
+            c = t.shape[-1]
+            g = old_grams[k] if k < len(old_grams) and old_grams[k].shape == (c, c) else \
+                torch.empty(c, c, device=self.device, dtype=torch.float32)
             ops.gram_loss_fwd(t, ws.gram_ws[k], gram_out=g)
             grams.append(g)
         if (sh, sw) != (ch, cw):
             del self._workspaces[(sh, sw)]  # style-sized buffers are never needed again
         ws = self._workspace(ch, cw, with_grad=False)
         self._run_stack(content_img.contiguous(), ws)
-        feats = [self._tap_tensor(ws, idx).clone() for idx in self.content_idx]
+        old_feats = self.content_targets_nhwc or []
+        feats = []
+        for k, idx in enumerate(self.content_idx):
+            t = self._tap_tensor(ws, idx)
+            if k < len(old_feats) and old_feats[k].shape == t.shape:
+                old_feats[k].copy_(t)
+                feats.append(old_feats[k])
+            else:
+                feats.append(t.clone())
         self.style_targets = grams
         self.content_targets_nhwc = feats
 

@@ -279,3 +279,41 @@ def test_1080p_step_properties(cuda_device) -> None:  # noqa: ANN001
     assert outs[0][0][-1] == 0.0
     assert all(v > 0 and np.isfinite(v) for v in outs[0][0][:-1])
     assert bool(torch.isfinite(outs[0][1]).all())
+
+
+def test_job_runner_reuses_graph_and_matches_fresh_runs(cuda_device) -> None:  # noqa: ANN001
+    """StyleJobRunner streams jobs through ONE captured graph (targets, image and Adam state are
+    overwritten in place): every job must give the same result as a freshly built model + runner."""
+    import style_transfer_visualizer_b200.core_model as cm
+    from oracle import stv_oracle as orc
+    from style_transfer_visualizer_b200 import jobs
+    from style_transfer_visualizer_b200.config import StyleTransferConfig
+    from style_transfer_visualizer_b200.optim import FusedAdam
+    from style_transfer_visualizer_b200.optimization import OptimizationRunner
+
+    def fresh_model():  # noqa: ANN202
+        original = cm.initialize_vgg
+        cm.initialize_vgg = lambda: orc.vgg19_features(0)
+        try:
+            return cm.StyleContentModel([0, 5, 10, 19, 28], [21]).to(cuda_device)
+        finally:
+            cm.initialize_vgg = original
+
+    runner = jobs.StyleJobRunner(fresh_model(), 64, 96, steps=4, lr=0.01, device=cuda_device)
+    pairs = [(orc.synthetic_image(10 + 2 * j, 64, 96), orc.synthetic_image(11 + 2 * j, 64, 96))
+             for j in range(3)]
+    results = [runner.run_job(c, s) for c, s in pairs]
+    assert runner.jobs_done == 3
+    graph_obj = runner._fused.graph  # noqa: SLF001
+    for (content, style), (img, loss) in zip(pairs, results):
+        model = fresh_model()
+        model.set_targets(style.to(cuda_device), content.to(cuda_device))
+        x = content.to(cuda_device).clone().requires_grad_(True)
+        cfg = StyleTransferConfig.model_validate({
+            "optimization": {"steps": 4, "style_w": 1e5, "content_w": 1.0, "lr": 0.01},
+            "video": {"save_every": 5}, "output": {"log_every": 1}})
+        _, hist, _ = OptimizationRunner(model, x, cfg, optimizer=FusedAdam([x], lr=0.01),
+                                        progress_bar=_gpu_run.NullBar()).run()
+        assert torch.equal(img.to(cuda_device), x.detach())
+        assert loss == hist["total_loss"][-1]
+    assert runner._fused.graph is graph_obj  # noqa: SLF001
