@@ -163,6 +163,12 @@ int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int 
                        const float* bias, const float* alpha, const float* mask_src,
                        const float* add_src, float* out_pre, float* out_post, int block_n,
                        int m_halves, int tw, void* stream);
+/* Tuning knobs of the tensor-core conv (process-wide; tests and sweeps).  pair_mode: 1 = run every
+ * layer on CTA pairs (clusters of two CTAs, tcgen05 cta_group::2: M = 256 per instruction, each CTA
+ * stages half of every weight tile), 0 = single-CTA tiles only, -1 = the built-in per-shape rule
+ * table (default).  a_stages / b_stages (operand ring depths) and taps_per_stage (1 or 3 weight taps
+ * per ring stage): 0 = built-in defaults. */
+int stv_conv_set_tuning(int pair_mode, int a_stages, int b_stages, int taps_per_stage);
 /* Naive CUDA-core NHWC conv, same packed weights; on-device cross-check only. */
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream);

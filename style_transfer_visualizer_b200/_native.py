@@ -60,6 +60,7 @@ _SIGNATURES: dict[str, list] = {
                           _vp],
     "stv_conv_igemm2_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                            _vp],
+    "stv_conv_set_tuning": [_i, _i, _i, _i],
     "stv_conv_ref": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"stv_gram_workspace_bytes": _sz, "stv_lbfgs_workspace_floats": _sz}

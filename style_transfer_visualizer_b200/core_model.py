@@ -93,13 +93,19 @@ def gram_matrix(tensor: torch.Tensor, clamp_max: float = GRAM_MATRIX_CLAMP_MAX) 
     b, c, h, w = tensor.size()
     nat.require_device(tensor.device)
     ch = b * c
-    if ch != 64 and ch % 128 != 0:
-        msg = f"gram_matrix: batch*channels must be 64 or a multiple of 128, got {ch}"
-        raise ValueError(msg)
-    feats = tensor.detach().to(torch.float32).reshape(ch, h * w).t().contiguous()  # [hw, ch]
-    work = ops.gram_workspace(h * w, ch, tensor.device)
-    out = torch.empty(ch, ch, device=tensor.device, dtype=torch.float32)
+    # The kernel takes 64 or a multiple of 128 channels; other counts are zero-padded (zero
+    # channels add zero rows/columns to F F^T, which are sliced off again).  The 1/N uses the
+    # padded count inside the kernel, so rescale by padded/true.
+    padded = 64 if ch <= 64 else -(-ch // 128) * 128
+    feats = tensor.detach().to(torch.float32).reshape(ch, h * w).t()  # [hw, ch]
+    if padded != ch:
+        feats = torch.nn.functional.pad(feats, (0, padded - ch))
+    feats = feats.contiguous()
+    work = ops.gram_workspace(h * w, padded, tensor.device)
+    out = torch.empty(padded, padded, device=tensor.device, dtype=torch.float32)
     ops.gram_loss_fwd(feats, work, gram_out=out, clamp_max=clamp_max)
+    if padded != ch:
+        out = out[:ch, :ch] * (padded / ch)
     return out
 
 

@@ -285,6 +285,15 @@ int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int 
   return conv_igemm2_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
                             out_post, 0, nullptr, block_n, m_halves, tw, S(stream));
 }
+int stv_conv_set_tuning(int pair_mode, int a_stages, int b_stages, int taps_per_stage) {
+  STV_REQUIRE(pair_mode >= -1 && pair_mode <= 1, "stv_conv_set_tuning: pair_mode must be -1, 0 or 1");
+  STV_REQUIRE(a_stages >= 0 && a_stages <= 8 && b_stages >= 0 && b_stages <= 16,
+              "stv_conv_set_tuning: ring depths out of range");
+  STV_REQUIRE(taps_per_stage == 0 || taps_per_stage == 1 || taps_per_stage == 3,
+              "stv_conv_set_tuning: taps_per_stage must be 0, 1 or 3");
+  conv_set_tuning(pair_mode, a_stages, b_stages, taps_per_stage);
+  return 0;
+}
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream) {
   return conv_ref_launch(x, w_packed, bias, H, W, C, N, taps, relu, out, S(stream));

@@ -15,6 +15,10 @@
 //     CTAs share weights in L2); operand rings keep streaming across tile boundaries and, when TMEM
 //     allows (2 * M_HALVES * BLOCK_N <= 512 columns), the accumulator is double-buffered so the
 //     epilogue of tile i overlaps the main loop of tile i+1.
+//   * PAIR variant (cluster of 2 CTAs, tcgen05 cta_group::2): the two CTAs of a pair own two
+//     different pixel patches but the SAME output-channel tile; each stages only HALF of every
+//     weight stage (BLOCK_N/2 rows) and the leader's M = 256 MMAs read both halves.  Weight
+//     traffic per CTA -- the larger share of the L2->SM stream that bounds this kernel -- halves.
 // Also hosts the N = 16 variant used for conv1_1's input gradient (64 -> 3 channels, written as
 // NCHW planes): the 3 real output channels are padded to the smallest legal UMMA N.
 #include <stdlib.h>
@@ -29,7 +33,7 @@ struct Conv2Params {
   int taps;            // 9 or 1
   int tw, th;          // CTA patch: th * tw == 128 * M_HALVES
   int tw_shift;        // log2(tw)
-  int tiles_x, tiles_m, tiles_total;
+  int tiles_x, tiles_m, tiles_total;  // PAIR: tiles_m counts PAIRS of patches (tiles_total too)
   int a_stage_bytes;   // (th + ndy - 1) * tw * 128, multiple of 1024
   int a_stages, b_stages;  // ring depths
   int tps;                 // weight taps per B stage (1 or 3): narrow N tiles batch the three dy taps
@@ -42,23 +46,30 @@ struct Conv2Params {
   float* out_post;
   int round_pre, round_post;
   float* out_nchw3;    // N == 16 variant: [3][H][W] planes
+  int debug;           // STV_CONV_DEBUG bits (bottleneck experiments; results are then garbage):
+                       // 1 skip weight loads, 2 skip activation loads, 4 skip stores, 8 skip MMAs
 };
 
 constexpr int kThreads2 = 192;
 
-template <int BLOCK_N, int MH>
+template <int BLOCK_N, int MH, bool PAIR>
 struct Conv2Cfg {
   static constexpr int kAcc = (2 * MH * BLOCK_N <= 512) ? 2 : 1;
   static constexpr int kTmemColsRaw = kAcc * MH * BLOCK_N;
   static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
-  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // weight rows staged by ONE CTA
+  static constexpr int kBBytes = kBRows * 128;
 };
 
-template <int BLOCK_N, int MH, int TPS>
+template <int BLOCK_N, int MH, int TPS, bool PAIR>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                         const __grid_constant__ CUtensorMap tmap_w, const Conv2Params p) {
-  using Cfg = Conv2Cfg<BLOCK_N, MH>;
+  using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR>;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // tile schedule: a "worker" is a CTA, or a CTA pair
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   constexpr int kAcc = Cfg::kAcc;
   const int AS = p.a_stages, BS = p.b_stages;
   const int num_bars = 2 * AS + 2 * BS + 2 * kAcc;
@@ -89,21 +100,33 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    for (int s = 0; s < kAcc; ++s) { mbar_init(acc_full + 8 * s, 1); mbar_init(acc_empty + 8 * s, 4); }
+    // PAIR: the leader's "full" barriers collect one expect_tx arrival from each CTA's producer,
+    // its "accumulator drained" barriers one arrival from each of the 2 x 4 epilogue warps
+    const uint32_t np = PAIR ? 2u : 1u;
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, np); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, np); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < kAcc; ++s) {
+      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_empty + 8 * s, 4 * np);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (warp >= 2 && BLOCK_N != 16) {
     for (int i = threadIdx.x - 64; i < p.N; i += kThreads2 - 64)
       sbias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must exist before remote arrives
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
@@ -117,25 +140,51 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-        const int nt = t / p.tiles_m, mt = t - nt * p.tiles_m;
+      // PAIR: completion bytes and the expect_tx arrival go to the LEADER's barrier
+      const uint32_t a_full_c = PAIR ? mapa_u32(a_full, 0) : a_full;
+      const uint32_t b_full_c = PAIR ? mapa_u32(b_full, 0) : b_full;
+      for (int t = worker; t < p.tiles_total; t += workers) {
+        const int nt = t / p.tiles_m;
+        const int mt = PAIR ? 2 * (t - nt * p.tiles_m) + static_cast<int>(rank) : t - nt * p.tiles_m;
+        // (an odd patch count leaves the last pair's second CTA a patch below the image: its
+        // loads are all out-of-bounds zero fill and its epilogue stores nothing)
         const int ty0 = (mt / p.tiles_x) * p.th, tx0 = (mt % p.tiles_x) * p.tw;
-        const int n0 = nt * BLOCK_N;
+        const int n0 = nt * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
             mbar_wait(a_empty + 8 * as, aph ^ 1);
-            mbar_expect_tx(a_full + 8 * as, p.a_stage_bytes);
-            tma_load_3d(a_base + as * p.a_stage_bytes, &tmap_x, a_full + 8 * as, c << 5,
-                        tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+            if (p.debug & 2) {
+              if constexpr (PAIR) mbar_arrive_cluster(a_full_c + 8 * as);
+              else mbar_arrive(a_full + 8 * as);
+            } else if constexpr (PAIR) {
+              mbar_expect_tx_cluster(a_full_c + 8 * as, p.a_stage_bytes);
+              tma_load_3d_pair(a_base + as * p.a_stage_bytes, &tmap_x, a_full_c + 8 * as, c << 5,
+                               tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+            } else {
+              mbar_expect_tx(a_full + 8 * as, p.a_stage_bytes);
+              tma_load_3d(a_base + as * p.a_stage_bytes, &tmap_x, a_full + 8 * as, c << 5,
+                          tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+            }
             if (++as == AS) { as = 0; aph ^= 1; }
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
               mbar_wait(b_empty + 8 * bs, bph ^ 1);
-              mbar_expect_tx(b_full + 8 * bs, TPS * Cfg::kBBytes);
+              if (p.debug & 1) {
+                if constexpr (PAIR) mbar_arrive_cluster(b_full_c + 8 * bs);
+                else mbar_arrive(b_full + 8 * bs);
+                if (++bs == BS) { bs = 0; bph ^= 1; }
+                continue;
+              }
+              if constexpr (PAIR) mbar_expect_tx_cluster(b_full_c + 8 * bs, TPS * Cfg::kBBytes);
+              else mbar_expect_tx(b_full + 8 * bs, TPS * Cfg::kBBytes);
 #pragma unroll
               for (int u = 0; u < TPS; ++u) {
                 const int tap = (dyi + u) * ndx + dxi;
-                tma_load_2d(b_base + (bs * TPS + u) * Cfg::kBBytes, &tmap_w, b_full + 8 * bs,
-                            c << 5, tap * p.N + n0);
+                if constexpr (PAIR)
+                  tma_load_2d_pair(b_base + (bs * TPS + u) * Cfg::kBBytes, &tmap_w,
+                                   b_full_c + 8 * bs, c << 5, tap * p.N + n0);
+                else
+                  tma_load_2d(b_base + (bs * TPS + u) * Cfg::kBBytes, &tmap_w, b_full + 8 * bs,
+                              c << 5, tap * p.N + n0);
               }
               if (++bs == BS) { bs = 0; bph ^= 1; }
             }
@@ -145,8 +194,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer -----------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(PAIR ? 256 : 128, BLOCK_N, 0, 0);
       // Descriptors: the upper word (SBO = 1024, version, SWIZZLE_128B) is constant; the lower word
       // is (address >> 4) | LBO, so every operand view is one 32-bit add away from the stage base.
       // The issue loop is a single thread's dependent instruction stream: for narrow N (32-64
@@ -157,8 +206,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       uint32_t aph = 0, bph = 0, accph = 0;
       const uint32_t row16 = static_cast<uint32_t>(row_bytes) >> 4;
       const uint32_t half16 = (128u >> p.tw_shift) * row16;  // rows per 128-pixel half
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-        mbar_wait(acc_empty + 8 * acc, accph ^ 1);  // epilogue has drained this accumulator
+      for (int t = worker; t < p.tiles_total; t += workers) {
+        // epilogue (of both CTAs) has drained this accumulator
+        if constexpr (PAIR) mbar_wait_cluster(acc_empty + 8 * acc, accph ^ 1);
+        else mbar_wait(acc_empty + 8 * acc, accph ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * (MH * BLOCK_N);
         uint32_t accum = 0;
@@ -169,7 +220,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
               mbar_wait(b_full + 8 * bs, bph);
-              tc_fence_after();
+              if (!(p.debug & 16)) tc_fence_after();
               const uint32_t b_lo =
                   (((b_base + bs * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
@@ -180,22 +231,30 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   const uint32_t bv = b_lo + u * (Cfg::kBBytes >> 4);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
+                    if (p.debug & 8) continue;
                     const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (av + 2 * k);
                     const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (bv + 2 * k);
-                    umma_tf32(d0 + hf * BLOCK_N, adesc, bdesc, idesc,
-                              (u == 0 && k == 0) ? accum : 1u);
+                    if constexpr (PAIR)
+                      umma_tf32_pair(d0 + hf * BLOCK_N, adesc, bdesc, idesc,
+                                     (u == 0 && k == 0) ? accum : 1u);
+                    else
+                      umma_tf32(d0 + hf * BLOCK_N, adesc, bdesc, idesc,
+                                (u == 0 && k == 0) ? accum : 1u);
                   }
                 }
                 if (u == 0) accum = 1;
               }
-              umma_commit(b_empty + 8 * bs);
+              if constexpr (PAIR) umma_commit_pair(b_empty + 8 * bs);
+              else umma_commit(b_empty + 8 * bs);
               if (++bs == BS) { bs = 0; bph ^= 1; }
             }
-            umma_commit(a_empty + 8 * as);
+            if constexpr (PAIR) umma_commit_pair(a_empty + 8 * as);
+            else umma_commit(a_empty + 8 * as);
             if (++as == AS) { as = 0; aph ^= 1; }
           }
         }
-        umma_commit(acc_full + 8 * acc);
+        if constexpr (PAIR) umma_commit_pair(acc_full + 8 * acc);
+        else umma_commit(acc_full + 8 * acc);
         if (++acc == kAcc) { acc = 0; accph ^= 1; }
       }
     }
@@ -205,8 +264,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     int acc = 0;
     uint32_t accph = 0;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-      const int nt = t / p.tiles_m, mt = t - nt * p.tiles_m;
+    const uint32_t acc_empty_c = PAIR ? mapa_u32(acc_empty, 0) : acc_empty;
+    for (int t = worker; t < p.tiles_total; t += workers) {
+      const int nt = t / p.tiles_m;
+      const int mt = PAIR ? 2 * (t - nt * p.tiles_m) + static_cast<int>(rank) : t - nt * p.tiles_m;
       const int ty0 = (mt / p.tiles_x) * p.th, tx0 = (mt % p.tiles_x) * p.tw;
       const int n0 = nt * BLOCK_N;
       mbar_wait(acc_full + 8 * acc, accph);
@@ -216,7 +277,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int m = hf * 128 + q * 32 + lane;
         const int py = ty0 + (m >> p.tw_shift);
         const int px = tx0 + (m & (p.tw - 1));
-        const bool valid = (py < p.H) && (px < p.W);
+        const bool valid = (py < p.H) && (px < p.W) && !(p.debug & 4);
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               acc * (MH * BLOCK_N) + hf * BLOCK_N;
         if constexpr (BLOCK_N == 16) {
@@ -376,33 +437,40 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       // release the accumulator to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + 8 * acc);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(acc_empty_c + 8 * acc);
+        else mbar_arrive(acc_empty + 8 * acc);
+      }
       if (++acc == kAcc) { acc = 0; accph ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may exit while the other can still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int block_n,
+// b_rows: weight rows one CTA stages per tap (the N tile, or half of it for a CTA pair)
+static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int b_rows,
                             int n_total) {
-  return as * a_stage_bytes + bs * tps * block_n * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
+  return as * a_stage_bytes + bs * tps * b_rows * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
          n_total * 4 + 128 + 4 * 4096;  // + bias + epilogue transpose tiles
 }
 
-template <int BLOCK_N, int MH, int TPS>
+template <int BLOCK_N, int MH, int TPS, bool PAIR>
 static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Params& p, int grid,
                    cudaStream_t stream) {
-  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS>;
-  const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, BLOCK_N, p.N);
+  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR>;
+  const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
+                                    Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -420,21 +488,58 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   cfg.blockDim = dim3(kThreads2);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
+  if (PAIR) {
+    // clusters of 2 cannot always use every SM (a GPC with an odd SM count strands one): size the
+    // persistent grid by what the device can co-schedule
+    static int max_clusters = -1;
+    static int max_clusters_smem = -1;
+    if (max_clusters < 0 || max_clusters_smem != smem) {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(2 * device_sm_count());
+      int n = 0;
+      STV_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+      STV_REQUIRE(n > 0, "conv_igemm2: no CTA pair of %d bytes fits the device", smem);
+      max_clusters = n;
+      max_clusters_smem = smem;
+    }
+    if (grid > 2 * max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+  }
   STV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, p));
   return 0;
+}
+
+static int g_pair_mode = -1;  // -1: rule table, 0: never, 1: whenever the shape allows
+static int g_as = 0, g_bs = 0, g_tps = 0;  // ring depth / taps-per-stage overrides (0 = defaults)
+void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
+  g_pair_mode = pair_mode;
+  g_as = a_stages;
+  g_bs = b_stages;
+  g_tps = tps;
 }
 
 // Tile selection (measured on B200, profiles/r1_selftest_perf_v2.log): N tile as wide as Cout
 // allows; 256-wide tiles run best with one 128-pixel half per CTA (double-buffered accumulator),
 // narrower tiles with two halves sharing each weight stage.  When that leaves SMs idle the tile is
 // narrowed.  tw is the patch width with the least padded area (ties: wider rows = smaller halo).
-struct TileChoice { int mh, tw, th, block_n; };
+struct TileChoice { int mh, tw, th, block_n, pair; };
 
+// number of CTA-sized work items (a CTA pair counts as two)
 static long count_tiles(int H, int W, int N, int mh, int tw, int bn) {
   const int th = 128 * mh / tw;
   return static_cast<long>((H + th - 1) / th) * ((W + tw - 1) / tw) * (N / bn);
@@ -459,7 +564,6 @@ static int pick_tw(int H, int W, int mh) {
 
 static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_epilogue,
                                int force_n, int force_mh, int force_tw) {
-  (void)taps;
   const int sms = device_sm_count();
   int bn, mh;
   if (N == 16) { bn = 16; mh = 1; }
@@ -483,7 +587,15 @@ static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_e
   if (force_n > 0) bn = force_n;
   if (force_mh > 0) mh = force_mh;
   const int tw = force_tw > 0 ? force_tw : pick_tw(H, W, mh);
-  return TileChoice{mh, tw, 128 * mh / tw, bn};
+  // CTA pairs (profiles/r1_pair_sweep.log): +5-11 % on 256-wide forward tiles, where each CTA then
+  // stages 128 weight rows and three taps fit a stage (12 MMAs per barrier round trip); neutral or
+  // worse for narrower tiles and for the read-heavy dgrad epilogue, which stay single-CTA.
+  int pair = 0;
+  if (N != 16) {
+    if (g_pair_mode >= 0) pair = g_pair_mode;
+    else pair = (bn == 256 && taps == 9 && !heavy_epilogue) ? 1 : 0;
+  }
+  return TileChoice{mh, tw, 128 * mh / tw, bn, pair};
 }
 
 int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
@@ -512,6 +624,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   p.tw_shift = tc.tw == 8 ? 3 : (tc.tw == 16 ? 4 : 5);
   p.tiles_x = (W + tc.tw - 1) / tc.tw;
   p.tiles_m = p.tiles_x * ((H + tc.th - 1) / tc.th);
+  if (tc.pair) p.tiles_m = (p.tiles_m + 1) / 2;  // pairs of patches
   p.tiles_total = p.tiles_m * (N / tc.block_n);
   const int halo = taps == 9 ? 2 : 0;
   p.a_stage_bytes = (tc.th + halo) * tc.tw * 128;
@@ -519,6 +632,10 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   p.out_pre = out_pre; p.out_post = out_post;
   p.round_pre = round_flags & 1; p.round_post = (round_flags >> 1) & 1;
   p.out_nchw3 = out_nchw3;
+  {
+    const char* e = getenv("STV_CONV_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
 
   CUtensorMap tx, twm;
   {
@@ -530,19 +647,23 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   {
     const uint64_t dims[2] = {(uint64_t)C, (uint64_t)taps * N};
     const uint64_t strides[1] = {(uint64_t)C * 4};
-    const uint32_t box[2] = {32, (uint32_t)tc.block_n};
+    const uint32_t box[2] = {32, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n)};
     if (int rc = encode_tmap_f32(&twm, w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
   }
   const int sms = device_sm_count();
   // ring depths: STV_CONV_STAGES="as,bs" overrides (experiments); defaults keep >= ~2000 MMA cycles
   // of weight stages in flight (TMA latency under load) within the shared-memory budget
-  static int env_as = -1, env_bs = -1, env_tps = -1;
-  if (env_as < 0) {
-    env_as = 0; env_bs = 0; env_tps = 0;
-    if (const char* e = getenv("STV_CONV_STAGES")) sscanf(e, "%d,%d,%d", &env_as, &env_bs, &env_tps);
+  static int env0_as = -1, env0_bs = -1, env0_tps = -1;
+  if (env0_as < 0) {
+    env0_as = 0; env0_bs = 0; env0_tps = 0;
+    if (const char* e = getenv("STV_CONV_STAGES"))
+      sscanf(e, "%d,%d,%d", &env0_as, &env0_bs, &env0_tps);
   }
-  p.tps = (taps == 9 && tc.block_n <= 128) ? 3 : 1;
-  if (env_tps > 0 && taps == 9 && tc.block_n <= 128) p.tps = env_tps;
+  const int env_as = g_as > 0 ? g_as : env0_as;
+  const int env_bs = g_bs > 0 ? g_bs : env0_bs;
+  const int env_tps = g_tps > 0 ? g_tps : env0_tps;
+  p.tps = (taps == 9 && (tc.block_n <= 128 || (tc.pair && tc.mh == 1))) ? 3 : 1;
+  if (env_tps > 0 && taps == 9 && (tc.block_n <= 128 || tc.pair)) p.tps = env_tps;
   if (p.tps == 3) {
     // measured (profiles/r1_stage_sweep.log): N=64 runs best as two co-resident CTAs with
     // 2-deep rings; N=128 with a 3-deep weight ring
@@ -552,23 +673,40 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
     p.a_stages = tc.block_n >= 256 ? 2 : 3;
     p.b_stages = 4;
   }
+  const int b_rows = tc.pair ? tc.block_n / 2 : tc.block_n;
+  if (tc.pair && p.tps == 1) p.b_stages = 6;
+  if (tc.pair && p.tps == 3 && tc.block_n == 256) p.b_stages = 3;  // half-size weight stages: same bytes in flight
   if (env_as > 0) p.a_stages = env_as;
   if (env_bs > 0) p.b_stages = env_bs;
-  while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, tc.block_n, N) >
+  while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N) >
              227 * 1024 && p.b_stages > 2)
     --p.b_stages;
-  const int smem_est =
-      conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, tc.block_n, N);
-  const int ctas_per_sm = smem_est <= 113 * 1024 ? 2 : 1;  // TMEM: <= 256 columns each
-  const int grid = p.tiles_total < sms * ctas_per_sm ? p.tiles_total : sms * ctas_per_sm;
+  const int smem_est = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N);
+  const int tmem_cols = (2 * tc.mh * tc.block_n <= 512 ? 2 : 1) * tc.mh * tc.block_n;
+  const int ctas_per_sm = (smem_est <= 113 * 1024 && tmem_cols <= 256) ? 2 : 1;
+  const int work_ctas = tc.pair ? 2 * p.tiles_total : p.tiles_total;
+  int grid = work_ctas < sms * ctas_per_sm ? work_ctas : sms * ctas_per_sm;
+  if (tc.pair) grid &= ~1;
 
-#define STV_L2(BN, MHV)                                                   \
-  if (tc.block_n == BN && tc.mh == MHV) {                                 \
-    if (p.tps == 3) return launch2<BN, MHV, 3>(tx, twm, p, grid, stream); \
-    return launch2<BN, MHV, 1>(tx, twm, p, grid, stream);                 \
+#define STV_L2(BN, MHV)                                                          \
+  if (tc.block_n == BN && tc.mh == MHV && !tc.pair) {                            \
+    if (p.tps == 3) return launch2<BN, MHV, 3, false>(tx, twm, p, grid, stream); \
+    return launch2<BN, MHV, 1, false>(tx, twm, p, grid, stream);                 \
   }
-  if (tc.block_n == 256 && tc.mh == 2) return launch2<256, 2, 1>(tx, twm, p, grid, stream);
-  if (tc.block_n == 256 && tc.mh == 1) return launch2<256, 1, 1>(tx, twm, p, grid, stream);
+#define STV_L2P(BN, MHV)                                                        \
+  if (tc.block_n == BN && tc.mh == MHV && tc.pair) {                            \
+    if (p.tps == 3) return launch2<BN, MHV, 3, true>(tx, twm, p, grid, stream); \
+    return launch2<BN, MHV, 1, true>(tx, twm, p, grid, stream);                 \
+  }
+  STV_L2P(256, 2)
+  STV_L2P(256, 1)
+  STV_L2P(128, 2)
+  STV_L2P(128, 1)
+  STV_L2P(64, 2)
+  STV_L2P(64, 1)
+#undef STV_L2P
+  if (tc.block_n == 256 && tc.mh == 2) return launch2<256, 2, 1, false>(tx, twm, p, grid, stream);
+  if (tc.block_n == 256 && tc.mh == 1) return launch2<256, 1, 1, false>(tx, twm, p, grid, stream);
   STV_L2(128, 2)
   STV_L2(128, 1)
   STV_L2(64, 2)

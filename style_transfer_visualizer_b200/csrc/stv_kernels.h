@@ -20,6 +20,10 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
                        float* out_nchw3, int force_n, int force_mh, int force_tw,
                        cudaStream_t stream);
 
+// pair_mode -1: built-in rule table; 0: single-CTA tiles only; 1: CTA pairs (cta_group::2) wherever
+// legal.  a_stages / b_stages / tps > 0 override the ring depths and weight taps per stage.
+void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps);
+
 // gram.cu ---------------------------------------------------------------------------------
 size_t gram_workspace_bytes(long hw, int C);
 int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspace_bytes,

@@ -280,3 +280,13 @@ def conv_ref(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None,
     nat.call("stv_conv_ref", nat.ptr(x), nat.ptr(w_packed), nat.ptr(bias), h, wd, c, n, taps,
              int(relu), nat.ptr(out), _s(x))
     return out
+
+
+def conv_set_tuning(pair_mode: int = -1, a_stages: int = 0, b_stages: int = 0, tps: int = 0) -> None:
+    """Process-wide conv tuning knobs (see ``stv_conv_set_tuning``); defaults restore the rule table."""
+    nat.call("stv_conv_set_tuning", int(pair_mode), int(a_stages), int(b_stages), int(tps))
+
+
+def conv_set_pair_mode(mode: int) -> None:
+    """-1: built-in rule table, 0: single-CTA conv tiles only, 1: CTA pairs wherever legal."""
+    conv_set_tuning(mode)

@@ -163,6 +163,17 @@ def test_model_surface_and_errors(cuda_device) -> None:  # noqa: ANN001
     assert g.shape == (128, 128)
     assert torch.allclose(g, g.t(), atol=1e-6)
     assert torch.linalg.eigvalsh(g.double()).min() >= -1e-6
+    # the reference's own Gram tests use a [1, 3, 100, 100] tensor (tests/test_core_model.py:33-96):
+    # any channel count and batch folding must work, clamp included
+    from oracle import stv_oracle as orc
+    for shape, scale in [((1, 3, 100, 100), 1.0), ((2, 3, 17, 13), 1.0), ((1, 200, 6, 7), 1.0),
+                         ((1, 3, 100, 100), 1e4)]:
+        t = torch.randn(*shape, generator=torch.Generator().manual_seed(5)) * scale
+        got = cm.gram_matrix(t.to(cuda_device)).cpu()
+        want = orc.gram_matrix(t)
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=2e-3, atol=2e-3 * float(want.abs().max()))
+        assert float(got.max()) <= 5e5 / t[0].numel() / shape[0] * 1.0001
     model.style_targets = None
     with pytest.raises(RuntimeError, match="style_targets must be set"):
         model(x0)
