@@ -103,7 +103,7 @@ def test_oracle_matches_live_reference() -> None:
     sl_b, cl_b = mine(xb)
     (1e5 * torch.stack(sl_a).sum() + torch.stack(cl_a).sum()).backward()
     (1e5 * torch.stack(sl_b).sum() + torch.stack(cl_b).sum()).backward()
-    assert [float(v) for v in sl_a] == [float(v) for v in sl_b]
+    assert [float(v.detach()) for v in sl_a] == [float(v.detach()) for v in sl_b]
     assert [float(v) for v in cl_a] == [float(v) for v in cl_b]
     assert torch.equal(xa.grad, xb.grad)
     assert torch.equal(ref.core_model.gram_matrix(x.repeat(1, 2, 1, 1)[:, :4]),
