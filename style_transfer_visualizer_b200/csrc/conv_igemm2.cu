@@ -50,7 +50,22 @@ struct Conv2Params {
                        // 1 skip weight loads, 2 skip activation loads, 4 skip stores, 8 skip MMAs
 };
 
-constexpr int kThreads2 = 192;
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  A warp may only read the TMEM lanes
+// 32*(warp%4)..+31, so epilogue warps come in groups of four; 128- and 256-wide tiles use two
+// groups, each draining half of the columns (the epilogue of a CTA's LAST tile is not overlapped
+// with anything, and on small feature maps every CTA has just one tile).
+#ifndef STV_EPI_WIDE
+#define STV_EPI_WIDE 1
+#endif
+// Issuing the first ring of (constant) weight stages BEFORE the programmatic-dependency wait was
+// measured neutral-to-negative (profiles/r1_conv_ab_epilogue_prefetch.log): off by default.
+#ifndef STV_PREFETCH_B
+#define STV_PREFETCH_B 0
+#endif
+__host__ __device__ constexpr int conv2_epi_warps(int block_n) {
+  return (STV_EPI_WIDE && block_n >= 128) ? 8 : 4;
+}
+__host__ __device__ constexpr int conv2_threads(int block_n) { return 64 + 32 * conv2_epi_warps(block_n); }
 
 template <int BLOCK_N, int MH, bool PAIR>
 struct Conv2Cfg {
@@ -62,10 +77,12 @@ struct Conv2Cfg {
 };
 
 template <int BLOCK_N, int MH, int TPS, bool PAIR>
-__global__ void __launch_bounds__(kThreads2, 1)
+__global__ void __launch_bounds__(conv2_threads(BLOCK_N), 1)
 conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                         const __grid_constant__ CUtensorMap tmap_w, const Conv2Params p) {
   using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR>;
+  constexpr int EW = conv2_epi_warps(BLOCK_N);
+  constexpr int kThreads2 = conv2_threads(BLOCK_N);
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // tile schedule: a "worker" is a CTA, or a CTA pair
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -101,13 +118,13 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     // PAIR: the leader's "full" barriers collect one expect_tx arrival from each CTA's producer,
-    // its "accumulator drained" barriers one arrival from each of the 2 x 4 epilogue warps
+    // its "accumulator drained" barriers one arrival from each epilogue warp of both CTAs
     const uint32_t np = PAIR ? 2u : 1u;
     for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, np); mbar_init(a_empty + 8 * s, 1); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, np); mbar_init(b_empty + 8 * s, 1); }
     for (int s = 0; s < kAcc; ++s) {
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, 4 * np);
+      mbar_init(acc_empty + 8 * s, EW * np);
     }
     fence_mbar_init();
   }
@@ -131,7 +148,32 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch, bias staging -- none of it touches activations) may overlap the tail of the previous
-  // kernel in the stream; from here on we read / write tensors it may still be using.
+  // kernel in the stream; so may the first ring of WEIGHT stages of a 3x3 conv (packed once, never
+  // rewritten; the 1x1 style-backward operand is produced inside the step and is not prefetched).
+  int b_pre = 0;
+  if (STV_PREFETCH_B && warp == 0 && lane == 0 && p.taps == 9 && !(p.debug & 1) &&
+      worker < p.tiles_total) {
+    const uint32_t b_full_c = PAIR ? mapa_u32(b_full, 0) : b_full;
+    const int n0 = (worker / p.tiles_m) * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
+    int c = 0, dxi = 0, dyi = 0;
+    for (; b_pre < BS && c < kc; ++b_pre) {
+      if constexpr (PAIR) mbar_expect_tx_cluster(b_full_c + 8 * b_pre, TPS * Cfg::kBBytes);
+      else mbar_expect_tx(b_full + 8 * b_pre, TPS * Cfg::kBBytes);
+#pragma unroll
+      for (int u = 0; u < TPS; ++u) {
+        const int tap = (dyi + u) * 3 + dxi;
+        if constexpr (PAIR)
+          tma_load_2d_pair(b_base + (b_pre * TPS + u) * Cfg::kBBytes, &tmap_w, b_full_c + 8 * b_pre,
+                           c << 5, tap * p.N + n0);
+        else
+          tma_load_2d(b_base + (b_pre * TPS + u) * Cfg::kBBytes, &tmap_w, b_full + 8 * b_pre,
+                      c << 5, tap * p.N + n0);
+      }
+      dyi += TPS;
+      if (dyi >= 3) { dyi = 0; if (++dxi == 3) { dxi = 0; ++c; } }
+    }
+  }
+  // From here on we read / write tensors the previous kernel may still be using.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -167,6 +209,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             }
             if (++as == AS) { as = 0; aph ^= 1; }
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
+              if (b_pre > 0) {  // this stage was issued before the dependency wait
+                --b_pre;
+                if (++bs == BS) { bs = 0; bph ^= 1; }
+                continue;
+              }
               mbar_wait(b_empty + 8 * bs, bph ^ 1);
               if (p.debug & 1) {
                 if constexpr (PAIR) mbar_arrive_cluster(b_full_c + 8 * bs);
@@ -261,6 +308,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   } else {
     // ------------------------------ epilogue -------------------------------------------------
     const int q = warp & 3;
+    constexpr int kCols = BLOCK_N / (EW / 4);      // columns drained by this warp
+    const int cb0 = ((warp - 2) >> 2) * kCols;
     int acc = 0;
     uint32_t accph = 0;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
@@ -305,7 +354,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             // thread, which L2 merges); cheaper than the transpose when nothing has to be read.
             const size_t row_off = (static_cast<size_t>(py) * p.W + px) * p.N + n0;
 #pragma unroll 1
-            for (int cb = 0; cb < BLOCK_N; cb += 32) {
+            for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
               uint32_t r[32];
               tmem_ld_32x32(trow + cb, r);
               tmem_ld_wait();
@@ -349,7 +398,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
           const uint32_t stg = stage_base + (warp - 2) * 4096;
           const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll 1
-          for (int cb = 0; cb < BLOCK_N; cb += 32) {
+          for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
             uint32_t r[32];
             tmem_ld_32x32(trow + cb, r);
             tmem_ld_wait();
@@ -459,10 +508,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 // host side
 // ---------------------------------------------------------------------------------------------
 // b_rows: weight rows one CTA stages per tap (the N tile, or half of it for a CTA pair)
+// staging: the transposing epilogue (ReLU gate / accumulate) needs one 4 KB tile per epilogue warp
 static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int b_rows,
-                            int n_total) {
+                            int n_total, int block_n, int staging) {
   return as * a_stage_bytes + bs * tps * b_rows * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
-         n_total * 4 + 128 + 4 * 4096;  // + bias + epilogue transpose tiles
+         n_total * 4 + 128 + (staging ? conv2_epi_warps(block_n) * 4096 : 0);
 }
 
 template <int BLOCK_N, int MH, int TPS, bool PAIR>
@@ -470,7 +520,8 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
                    cudaStream_t stream) {
   auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR>;
   const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
-                                    Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N);
+                                    Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N,
+                                    p.mask_src != nullptr || p.add_src != nullptr);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -485,7 +536,7 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads2);
+  cfg.blockDim = dim3(conv2_threads(BLOCK_N));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -678,10 +729,13 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   if (tc.pair && p.tps == 3 && tc.block_n == 256) p.b_stages = 3;  // half-size weight stages: same bytes in flight
   if (env_as > 0) p.a_stages = env_as;
   if (env_bs > 0) p.b_stages = env_bs;
-  while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N) >
-             227 * 1024 && p.b_stages > 2)
+  const int staging = mask_src != nullptr || add_src != nullptr;
+  while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N,
+                          tc.block_n, staging) > 227 * 1024 && p.b_stages > 2)
     --p.b_stages;
-  const int smem_est = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N);
+  const int smem_est =
+      conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N, tc.block_n,
+                       staging);
   const int tmem_cols = (2 * tc.mh * tc.block_n <= 512 ? 2 : 1) * tc.mh * tc.block_n;
   const int ctas_per_sm = (smem_est <= 113 * 1024 && tmem_cols <= 256) ? 2 : 1;
   const int work_ctas = tc.pair ? 2 * p.tiles_total : p.tiles_total;
