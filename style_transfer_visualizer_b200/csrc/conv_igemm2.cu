@@ -107,6 +107,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t stage_base =
       (bar_base + 8 * num_bars + 16 + static_cast<uint32_t>(p.N) * 4 + 127u) & ~127u;
 
+  const bool poll = (p.debug & 32) != 0;
+  auto WAIT = [poll](uint32_t bar, uint32_t parity) {
+    if (poll) mbar_wait_poll(bar, parity);
+    else mbar_wait(bar, parity);
+  };
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kc = p.C >> 5;
@@ -194,7 +199,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int n0 = nt * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
-            mbar_wait(a_empty + 8 * as, aph ^ 1);
+            WAIT(a_empty + 8 * as, aph ^ 1);
             if (p.debug & 2) {
               if constexpr (PAIR) mbar_arrive_cluster(a_full_c + 8 * as);
               else mbar_arrive(a_full + 8 * as);
@@ -214,7 +219,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 if (++bs == BS) { bs = 0; bph ^= 1; }
                 continue;
               }
-              mbar_wait(b_empty + 8 * bs, bph ^ 1);
+              WAIT(b_empty + 8 * bs, bph ^ 1);
               if (p.debug & 1) {
                 if constexpr (PAIR) mbar_arrive_cluster(b_full_c + 8 * bs);
                 else mbar_arrive(b_full + 8 * bs);
@@ -256,17 +261,17 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       for (int t = worker; t < p.tiles_total; t += workers) {
         // epilogue (of both CTAs) has drained this accumulator
         if constexpr (PAIR) mbar_wait_cluster(acc_empty + 8 * acc, accph ^ 1);
-        else mbar_wait(acc_empty + 8 * acc, accph ^ 1);
+        else WAIT(acc_empty + 8 * acc, accph ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * (MH * BLOCK_N);
         uint32_t accum = 0;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
-            mbar_wait(a_full + 8 * as, aph);
+            WAIT(a_full + 8 * as, aph);
             const uint32_t a_lo =
                 (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
-              mbar_wait(b_full + 8 * bs, bph);
+              WAIT(b_full + 8 * bs, bph);
               if (!(p.debug & 16)) tc_fence_after();
               const uint32_t b_lo =
                   (((b_base + bs * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
@@ -319,7 +324,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const int mt = PAIR ? 2 * (t - nt * p.tiles_m) + static_cast<int>(rank) : t - nt * p.tiles_m;
       const int ty0 = (mt / p.tiles_x) * p.th, tx0 = (mt % p.tiles_x) * p.tw;
       const int n0 = nt * BLOCK_N;
-      mbar_wait(acc_full + 8 * acc, accph);
+      WAIT(acc_full + 8 * acc, accph);
       tc_fence_after();
 #pragma unroll 1
       for (int hf = 0; hf < MH; ++hf) {
@@ -637,16 +642,19 @@ static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_e
   }
   if (force_n > 0) bn = force_n;
   if (force_mh > 0) mh = force_mh;
-  const int tw = force_tw > 0 ? force_tw : pick_tw(H, W, mh);
-  // CTA pairs (profiles/r1_pair_sweep.log): +5-11 % on 256-wide forward tiles, where each CTA then
-  // stages 128 weight rows and three taps fit a stage (12 MMAs per barrier round trip); neutral or
-  // worse for narrower tiles and for the read-heavy dgrad epilogue, which stay single-CTA.
+  // CTA pairs (profiles/r1_pair_sweep.log, r1_ring_sweep.log): with half-size weight stages a
+  // 256-wide tile affords three taps per stage (12 MMAs per barrier round trip) AND 3-deep rings;
+  // a stage is only re-armed a full commit -> producer -> TMA -> consumer chain (~1.7 us) after its
+  // MMAs retire, so ring depth x MMA time per stage must cover that chain.  +10-15 % on 256-wide
+  // tiles, +5 % on 128-wide two-half tiles; neutral or worse elsewhere, which stays single-CTA.
   int pair = 0;
   if (N != 16) {
     if (g_pair_mode >= 0) pair = g_pair_mode;
-    else pair = (bn == 256 && taps == 9 && !heavy_epilogue) ? 1 : 0;
+    else pair = (taps == 9 && (bn == 256 || (bn == 128 && mh == 2))) ? 1 : 0;
+    if (pair && bn == 256 && force_mh <= 0) mh = 1;
   }
-  return TileChoice{mh, tw, 128 * mh / tw, bn, pair};
+  const int tw2 = force_tw > 0 ? force_tw : pick_tw(H, W, mh);
+  return TileChoice{mh, tw2, 128 * mh / tw2, bn, pair};
 }
 
 int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
@@ -713,7 +721,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   const int env_as = g_as > 0 ? g_as : env0_as;
   const int env_bs = g_bs > 0 ? g_bs : env0_bs;
   const int env_tps = g_tps > 0 ? g_tps : env0_tps;
-  p.tps = (taps == 9 && (tc.block_n <= 128 || (tc.pair && tc.mh == 1))) ? 3 : 1;
+  p.tps = (taps == 9 && (tc.block_n <= 128 || tc.pair)) ? 3 : 1;
   if (env_tps > 0 && taps == 9 && (tc.block_n <= 128 || tc.pair)) p.tps = env_tps;
   if (p.tps == 3) {
     // measured (profiles/r1_stage_sweep.log): N=64 runs best as two co-resident CTAs with
@@ -725,8 +733,8 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
     p.b_stages = 4;
   }
   const int b_rows = tc.pair ? tc.block_n / 2 : tc.block_n;
-  if (tc.pair && p.tps == 1) p.b_stages = 6;
-  if (tc.pair && p.tps == 3 && tc.block_n == 256) p.b_stages = 3;  // half-size weight stages: same bytes in flight
+  if (tc.pair && p.tps == 1) p.b_stages = 6;  // half-size weight stages: same bytes in flight
+  if (tc.pair && p.tps == 3 && tc.block_n >= 128) { p.a_stages = 3; p.b_stages = 3; }
   if (env_as > 0) p.a_stages = env_as;
   if (env_bs > 0) p.b_stages = env_bs;
   const int staging = mask_src != nullptr || add_src != nullptr;
