@@ -38,6 +38,10 @@ struct Conv2Params {
   int a_stages, b_stages;  // ring depths
   int tps;                 // weight taps per B stage (1 or 3): narrow N tiles batch the three dy taps
                            // of one dx into a stage so the MMA thread synchronises 3x less often
+  int uni;                 // unified ring: one weight stage per activation stage (tps == 3, or a 1x1
+                           // conv), so stage s = {A tile, its weight taps} behind ONE full / empty
+                           // barrier pair.  tcgen05.commit stalls the issuing thread for ~350
+                           // cycles (profiles/r1_conv_bottleneck.log): one commit per 12 MMAs, not two
   const float* bias;
   const float* alpha;
   const float* mask_src;
@@ -156,7 +160,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   // kernel in the stream; so may the first ring of WEIGHT stages of a 3x3 conv (packed once, never
   // rewritten; the 1x1 style-backward operand is produced inside the step and is not prefetched).
   int b_pre = 0;
-  if (STV_PREFETCH_B && warp == 0 && lane == 0 && p.taps == 9 && !(p.debug & 1) &&
+  if (STV_PREFETCH_B && !p.uni && warp == 0 && lane == 0 && p.taps == 9 && !(p.debug & 1) &&
       worker < p.tiles_total) {
     const uint32_t b_full_c = PAIR ? mapa_u32(b_full, 0) : b_full;
     const int n0 = (worker / p.tiles_m) * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
@@ -200,45 +204,60 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
             WAIT(a_empty + 8 * as, aph ^ 1);
-            if (p.debug & 2) {
-              if constexpr (PAIR) mbar_arrive_cluster(a_full_c + 8 * as);
-              else mbar_arrive(a_full + 8 * as);
+            const int cur = as;
+            const uint32_t a_bytes = (p.debug & 2) ? 0u : static_cast<uint32_t>(p.a_stage_bytes);
+            const uint32_t b_bytes = (p.debug & 1) ? 0u : static_cast<uint32_t>(TPS * Cfg::kBBytes);
+            const uint32_t tx_a = a_bytes + (p.uni ? b_bytes : 0u);
+            if (tx_a == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(a_full_c + 8 * cur);
+              else mbar_arrive(a_full + 8 * cur);
             } else if constexpr (PAIR) {
-              mbar_expect_tx_cluster(a_full_c + 8 * as, p.a_stage_bytes);
-              tma_load_3d_pair(a_base + as * p.a_stage_bytes, &tmap_x, a_full_c + 8 * as, c << 5,
-                               tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+              mbar_expect_tx_cluster(a_full_c + 8 * cur, tx_a);
             } else {
-              mbar_expect_tx(a_full + 8 * as, p.a_stage_bytes);
-              tma_load_3d(a_base + as * p.a_stage_bytes, &tmap_x, a_full + 8 * as, c << 5,
-                          tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+              mbar_expect_tx(a_full + 8 * cur, tx_a);
+            }
+            if (a_bytes) {
+              if constexpr (PAIR)
+                tma_load_3d_pair(a_base + cur * p.a_stage_bytes, &tmap_x, a_full_c + 8 * cur, c << 5,
+                                 tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+              else
+                tma_load_3d(a_base + cur * p.a_stage_bytes, &tmap_x, a_full + 8 * cur, c << 5,
+                            tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
             }
             if (++as == AS) { as = 0; aph ^= 1; }
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
-              if (b_pre > 0) {  // this stage was issued before the dependency wait
-                --b_pre;
+              uint32_t slot, bar_l, bar_c;   // weight slot and the barrier its bytes are credited to
+              if (p.uni) {
+                slot = cur; bar_l = a_full + 8 * cur; bar_c = a_full_c + 8 * cur;
+              } else {
+                if (b_pre > 0) {  // this stage was issued before the dependency wait
+                  --b_pre;
+                  if (++bs == BS) { bs = 0; bph ^= 1; }
+                  continue;
+                }
+                WAIT(b_empty + 8 * bs, bph ^ 1);
+                slot = bs; bar_l = b_full + 8 * bs; bar_c = b_full_c + 8 * bs;
                 if (++bs == BS) { bs = 0; bph ^= 1; }
-                continue;
+                if (b_bytes == 0) {
+                  if constexpr (PAIR) mbar_arrive_cluster(bar_c);
+                  else mbar_arrive(bar_l);
+                } else if constexpr (PAIR) {
+                  mbar_expect_tx_cluster(bar_c, b_bytes);
+                } else {
+                  mbar_expect_tx(bar_l, b_bytes);
+                }
               }
-              WAIT(b_empty + 8 * bs, bph ^ 1);
-              if (p.debug & 1) {
-                if constexpr (PAIR) mbar_arrive_cluster(b_full_c + 8 * bs);
-                else mbar_arrive(b_full + 8 * bs);
-                if (++bs == BS) { bs = 0; bph ^= 1; }
-                continue;
-              }
-              if constexpr (PAIR) mbar_expect_tx_cluster(b_full_c + 8 * bs, TPS * Cfg::kBBytes);
-              else mbar_expect_tx(b_full + 8 * bs, TPS * Cfg::kBBytes);
+              if (b_bytes == 0) continue;
 #pragma unroll
               for (int u = 0; u < TPS; ++u) {
                 const int tap = (dyi + u) * ndx + dxi;
                 if constexpr (PAIR)
-                  tma_load_2d_pair(b_base + (bs * TPS + u) * Cfg::kBBytes, &tmap_w,
-                                   b_full_c + 8 * bs, c << 5, tap * p.N + n0);
+                  tma_load_2d_pair(b_base + (slot * TPS + u) * Cfg::kBBytes, &tmap_w, bar_c, c << 5,
+                                   tap * p.N + n0);
                 else
-                  tma_load_2d(b_base + (bs * TPS + u) * Cfg::kBBytes, &tmap_w, b_full + 8 * bs,
-                              c << 5, tap * p.N + n0);
+                  tma_load_2d(b_base + (slot * TPS + u) * Cfg::kBBytes, &tmap_w, bar_l, c << 5,
+                              tap * p.N + n0);
               }
-              if (++bs == BS) { bs = 0; bph ^= 1; }
             }
           }
         }
@@ -271,10 +290,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             const uint32_t a_lo =
                 (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
-              WAIT(b_full + 8 * bs, bph);
+              if (!p.uni) WAIT(b_full + 8 * bs, bph);
               if (!(p.debug & 16)) tc_fence_after();
+              const uint32_t b_slot = p.uni ? as : bs;
               const uint32_t b_lo =
-                  (((b_base + bs * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
+                  (((b_base + b_slot * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
               for (int u = 0; u < TPS; ++u) {
 #pragma unroll
@@ -296,9 +316,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 }
                 if (u == 0) accum = 1;
               }
-              if constexpr (PAIR) umma_commit_pair(b_empty + 8 * bs);
-              else umma_commit(b_empty + 8 * bs);
-              if (++bs == BS) { bs = 0; bph ^= 1; }
+              if (!p.uni) {
+                if constexpr (PAIR) umma_commit_pair(b_empty + 8 * bs);
+                else umma_commit(b_empty + 8 * bs);
+                if (++bs == BS) { bs = 0; bph ^= 1; }
+              }
             }
             if constexpr (PAIR) umma_commit_pair(a_empty + 8 * as);
             else umma_commit(a_empty + 8 * as);
@@ -723,24 +745,42 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   const int env_tps = g_tps > 0 ? g_tps : env0_tps;
   p.tps = (taps == 9 && (tc.block_n <= 128 || tc.pair)) ? 3 : 1;
   if (env_tps > 0 && taps == 9 && (tc.block_n <= 128 || tc.pair)) p.tps = env_tps;
-  if (p.tps == 3) {
-    // measured (profiles/r1_stage_sweep.log): N=64 runs best as two co-resident CTAs with
-    // 2-deep rings; N=128 with a 3-deep weight ring
-    p.a_stages = 2;
-    p.b_stages = tc.block_n == 64 ? 2 : (tc.block_n == 16 ? 4 : 3);
-  } else {
-    p.a_stages = tc.block_n >= 256 ? 2 : 3;
-    p.b_stages = 4;
+  static int env_uni = -1;
+  if (env_uni < 0) {
+    const char* e = getenv("STV_CONV_UNI");
+    env_uni = (e && e[0] == '0') ? 0 : 1;
   }
   const int b_rows = tc.pair ? tc.block_n / 2 : tc.block_n;
-  if (tc.pair && p.tps == 1) p.b_stages = 6;  // half-size weight stages: same bytes in flight
-  if (tc.pair && p.tps == 3 && tc.block_n >= 128) { p.a_stages = 3; p.b_stages = 3; }
-  if (env_as > 0) p.a_stages = env_as;
-  if (env_bs > 0) p.b_stages = env_bs;
   const int staging = mask_src != nullptr || add_src != nullptr;
-  while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N,
-                          tc.block_n, staging) > 227 * 1024 && p.b_stages > 2)
-    --p.b_stages;
+  p.uni = (env_uni && (taps == 1 || p.tps == 3)) ? 1 : 0;
+  if (p.uni) {
+    // one ring of {A tile, its weight taps}: as deep as shared memory allows, up to 4; 64-wide and
+    // 16-wide tiles stay at 2 so that two CTAs share an SM
+    int depth = tc.block_n == 64 ? 2 : 4;
+    if (env_as > 0) depth = env_as;
+    while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, depth, depth, p.tps, b_rows, N,
+                                         tc.block_n, staging) > 227 * 1024)
+      --depth;
+    p.a_stages = depth;
+    p.b_stages = depth;
+  } else {
+    if (p.tps == 3) {
+      // measured (profiles/r1_stage_sweep.log): N=64 runs best as two co-resident CTAs with
+      // 2-deep rings; N=128 with a 3-deep weight ring
+      p.a_stages = 2;
+      p.b_stages = tc.block_n == 64 ? 2 : (tc.block_n == 16 ? 4 : 3);
+    } else {
+      p.a_stages = tc.block_n >= 256 ? 2 : 3;
+      p.b_stages = 4;
+    }
+    if (tc.pair && p.tps == 1) p.b_stages = 6;  // half-size weight stages: same bytes in flight
+    if (tc.pair && p.tps == 3 && tc.block_n >= 128) { p.a_stages = 3; p.b_stages = 3; }
+    if (env_as > 0) p.a_stages = env_as;
+    if (env_bs > 0) p.b_stages = env_bs;
+    while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N,
+                            tc.block_n, staging) > 227 * 1024 && p.b_stages > 2)
+      --p.b_stages;
+  }
   const int smem_est =
       conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N, tc.block_n,
                        staging);
