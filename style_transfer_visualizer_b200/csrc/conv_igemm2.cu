@@ -647,7 +647,7 @@ static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_e
   if (N == 16) { bn = 16; mh = 1; }
   else if (N % 256 == 0) { bn = 256; mh = (C >= 512 && !heavy_epilogue) ? 2 : 1; }
   else if (N % 128 == 0) { bn = 128; mh = 2; }
-  else { bn = 64; mh = 1; }
+  else { bn = 64; mh = heavy_epilogue ? 1 : 2; }  // fwd: 24 MMAs per commit beat two co-resident CTAs
   if (force_n <= 0 && force_mh <= 0 && N != 16) {
     // keep the machine busy on small feature maps: narrow the tile until ~every SM has one
     const int order[5][2] = {{256, 2}, {256, 1}, {128, 2}, {128, 1}, {64, 1}};
@@ -756,7 +756,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   if (p.uni) {
     // one ring of {A tile, its weight taps}: as deep as shared memory allows, up to 4; 64-wide and
     // 16-wide tiles stay at 2 so that two CTAs share an SM
-    int depth = tc.block_n == 64 ? 2 : 4;
+    int depth = (tc.block_n == 64 && tc.mh == 1) ? 2 : 4;
     if (env_as > 0) depth = env_as;
     while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, depth, depth, p.tps, b_rows, N,
                                          tc.block_n, staging) > 227 * 1024)

@@ -21,6 +21,8 @@ def cands(n):
                 out.append((bn, mh, 1, 0, 0, tps))
             if bn <= 128:
                 out.append((bn, mh, 0, 0, 0, 0))
+                out.append((bn, mh, 0, 3, 3, 0))
+                out.append((bn, mh, 0, 4, 4, 0))
     return out
 for (h, w, c, n) in layers:
     x = torch.randn(h, w, c, device=dev, generator=g)
@@ -48,7 +50,7 @@ for (h, w, c, n) in layers:
             for _ in range(8): f()
             b.record(); torch.cuda.synchronize()
             ms = a.elapsed_time(b) / 8
-            rows.append((ms, f"bn{bn} mh{mh} pair{pair} tps{tps}: {ms*1e3:7.1f} us {2.0*h*w*c*n*9/ms/1e9:6.1f} TF/s"))
+            rows.append((ms, f"bn{bn} mh{mh} pair{pair} tps{tps} as{as_}: {ms*1e3:7.1f} us {2.0*h*w*c*n*9/ms/1e9:6.1f} TF/s"))
         base = rows[0][0]
         rows_sorted = sorted(rows[1:])[:4]
         print(f"{h}x{w} C{c}->N{n} heavy={heavy}: rule {rows[0][1]}", flush=True)
