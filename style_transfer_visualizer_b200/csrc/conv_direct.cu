@@ -23,6 +23,9 @@ __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                       const float* __restrict__ bias, int H, int W, int groups_per_row,
                       int round_pre, float* __restrict__ out_pre, float* __restrict__ out_post) {
+  // let a following tensor-core conv (launched with programmatic stream serialization) run its
+  // prologue under this kernel's tail; it still waits for our completion before touching data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float4 ws[27][kFirstCout / 4];  // ws[k][c/4] = w[c..c+3][k], k = ci*9 + ky*3 + kx
   __shared__ float4 bs[kFirstCout / 4];
   for (int i = threadIdx.x; i < 27 * kFirstCout; i += 128) {

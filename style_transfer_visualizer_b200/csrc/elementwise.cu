@@ -44,6 +44,9 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, float* __r
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 maxpool2_fwd_kernel(const float4* __restrict__ x, int H, int W, int C4, float4* __restrict__ y) {
+  // let a following tensor-core conv (launched with programmatic stream serialization) run its
+  // prologue under this kernel's tail; it still waits for our completion before touching data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int Ho = H >> 1, Wo = W >> 1;
   const long total = static_cast<long>(Ho) * Wo * C4;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -76,6 +79,9 @@ maxpool2_fwd_kernel(const float4* __restrict__ x, int H, int W, int C4, float4* 
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, int H, int W,
                     int C4, int relu_mask, float4* __restrict__ dx) {
+  // let a following tensor-core conv (launched with programmatic stream serialization) run its
+  // prologue under this kernel's tail; it still waits for our completion before touching data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int Ho = H >> 1, Wo = W >> 1;
   const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
   const long total = static_cast<long>(Hc) * Wc * C4;
