@@ -23,3 +23,47 @@ def test_kernel_case(case: str) -> None:
     assert proc.returncode == 0 and not fails, \
         "\n".join(fails) + "\n" + proc.stdout[-3000:] + proc.stderr[-3000:]
     assert proc.stdout.count("PASS") > 5
+
+
+@pytest.mark.gpu
+def test_conv_cta_pair_matches_single_cta_bit_for_bit(cuda_device) -> None:  # noqa: ANN001
+    """The cta_group::2 variant (M = 256 per instruction, weight tile split over two CTAs' shared
+    memory) accumulates every output in the same K order as the single-CTA kernel: identical bits,
+    for every tile shape, ring depth and taps-per-stage setting, ragged sizes and an odd patch
+    count (last pair half empty) included; and both agree with the CUDA-core cross-check."""
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    try:
+        for h, w, c, n in [(33, 47, 128, 256), (24, 40, 256, 128), (19, 21, 64, 64), (16, 16, 512, 512)]:
+            x = torch.randn(h, w, c, device=cuda_device, generator=g)
+            wt = torch.randn(n, c, 3, 3, device=cuda_device, generator=g) * 0.05
+            wf, _ = ops.pack_conv_weights(wt)
+            bias = torch.randn(n, device=cuda_device, generator=g)
+            mask = torch.randn(h, w, n, device=cuda_device, generator=g)
+            add = torch.randn(h, w, n, device=cuda_device, generator=g)
+            ref = ops.conv_ref(x, wf, bias, taps=9, relu=False)
+            for bn in (256, 128, 64):
+                if n % bn:
+                    continue
+                for mh in (1, 2):
+                    outs = []
+                    for pair, depth, tps in [(0, 0, 0), (1, 0, 0), (1, 2, 1), (1, 3, 3), (0, 3, 1)]:
+                        ops.conv_set_tuning(pair, depth, depth, tps)
+                        pre = torch.full((h, w, n), float("nan"), device=cuda_device)
+                        post = torch.full((h, w, n), float("nan"), device=cuda_device)
+                        ops.conv_igemm2_ex(x, wf, taps=9, bias=bias, out_pre=pre, out_post=post,
+                                           block_n=bn, m_halves=mh)
+                        heavy = torch.full((h, w, n), float("nan"), device=cuda_device)
+                        ops.conv_igemm2_ex(x, wf, taps=9, mask_src=mask, add_src=add, out_pre=heavy,
+                                           block_n=bn, m_halves=mh)
+                        outs.append((pre, post, heavy))
+                    for o in outs[1:]:
+                        for a, b in zip(outs[0], o):
+                            assert torch.equal(a, b)
+                    assert torch.allclose(outs[0][0], ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+                    assert torch.equal(outs[0][1], torch.relu(outs[0][0]))
+    finally:
+        ops.conv_set_tuning()

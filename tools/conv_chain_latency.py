@@ -1,3 +1,5 @@
+"""Handoff-chain experiment: one 64x64 512->512 conv under STV_CONV_DEBUG modes (15 = control skeleton
+only, 7 = MMAs only, 3 = no loads, 0 = full) for several ring configurations (profiles/r1_conv_chain_latency.log)."""
 import os, sys, subprocess
 code = r'''
 import sys, os, torch

@@ -1,3 +1,4 @@
+"""Ring depth / CTA-pair sweep on representative layers (profiles/r1_ring_sweep.log)."""
 import sys, torch
 sys.path.insert(0, ".")
 from style_transfer_visualizer_b200 import ops
