@@ -467,15 +467,25 @@ def run_jobs_arm(args, wl) -> None:  # noqa: ANN001
         model = cm.StyleContentModel([0, 5, 10, 19, 28], [21])
     finally:
         cm.initialize_vgg = original
-    runner = jobs.StyleJobRunner(model, wl["h"], wl["w"], steps=steps, lr=LR, style_w=STYLE_W,
-                                 content_w=CONTENT_W, device=device)
+    lanes = max(1, args.lanes)
+
+    def make_model():  # noqa: ANN202
+        cm.initialize_vgg = lambda: synthetic.random_vgg19_features(0)
+        try:
+            return cm.StyleContentModel([0, 5, 10, 19, 28], [21])
+        finally:
+            cm.initialize_vgg = original
+
+    models = iter([model] + [make_model() for _ in range(lanes - 1)])
+    pool = jobs.StyleJobPool(lambda: next(models), wl["h"], wl["w"], steps=steps, lanes=lanes,
+                             lr=LR, style_w=STYLE_W, content_w=CONTENT_W, device=device)
     pairs = [(synthetic.synthetic_image(1 + 2 * j, wl["h"], wl["w"]),
               synthetic.synthetic_image(2 + 2 * j, wl["h"], wl["w"])) for j in mine]
-    runner.run_job(*pairs[0])  # warm-up job: workspace allocation + graph capture
+    pool.run(pairs[:lanes])  # warm-up wave: workspace allocation + graph capture in every lane
     torch.cuda.synchronize(device)
     jobs.barrier()
     t0 = time.perf_counter()
-    losses = [runner.run_job(c, s)[1] for c, s in pairs]
+    losses = [r[1] for r in pool.run(pairs)]
     torch.cuda.synchronize(device)
     local = time.perf_counter() - t0
     jobs.barrier()
@@ -487,6 +497,7 @@ def run_jobs_arm(args, wl) -> None:  # noqa: ANN001
             "ms_per_step": total_s / (len(mine) * steps) * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": wl["name"], "jobs": n_jobs, "jobs_per_gpu": len(mine),
+                       "concurrent_lanes_per_gpu": lanes,
                        "steps_per_job": steps, "height": wl["h"], "width": wl["w"],
                        "timing": "host wall clock per rank over its jobs (H2D of both images and "
                                  "D2H of the result inside), max over ranks"},
@@ -604,6 +615,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="jobs64 workload: independent jobs in flight per GPU (own stream + graph)")
     ap.add_argument("--sharded-graph", type=int, default=1,
                     help="4k workload: replay the sharded step from a CUDA graph (0 = eager)")
     args = ap.parse_args()

@@ -149,8 +149,60 @@ class StyleJobRunner:
         self._load(content, style)
         for _ in range(self.steps):
             self._fused.step()
-        loss = self._fused.scores[2]
+        self._finish_async()
+        return self._collect()
+
+    def _finish_async(self) -> None:
+        """Queue the result readback on the current stream (no host synchronisation)."""
         self._pin_out.copy_(self.x.detach(), non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        self._loss_host = self._fused.scores[2:3].to("cpu", non_blocking=True)
+        self._done = torch.cuda.Event()
+        self._done.record()
+
+    def _collect(self) -> tuple[torch.Tensor, float]:
+        self._done.synchronize()
         self.jobs_done += 1
-        return self._pin_out.clone(), float(loss)
+        return self._pin_out.clone(), float(self._loss_host[0])
+
+
+class StyleJobPool:
+    """Several ``StyleJobRunner`` lanes on ONE GPU, each on its own stream with its own model copy,
+    workspaces and captured step graph; the jobs' step graphs are replayed interleaved.  A 512x512
+    step is a dependent chain of 15-60 us kernels that leave 20-odd SMs idle on the small feature
+    maps and pay launch / prologue / epilogue latency at every link; a second independent chain
+    fills those holes, so aggregate throughput of a batch of jobs (BASELINE.json configs[3]) is
+    higher than running them one after the other.  Results are bit-identical to the sequential
+    runner's (deterministic kernels, no shared state between lanes)."""
+
+    def __init__(self, make_model, height: int, width: int, *, steps: int, lanes: int = 2,  # noqa: ANN001
+                 device: torch.device | None = None, **runner_kwargs) -> None:  # noqa: ANN003
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.steps = steps
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
+        self.runners = [StyleJobRunner(make_model(), height, width, steps=steps, device=self.device,
+                                       **runner_kwargs) for _ in range(lanes)]
+
+    def run(self, pairs: list[tuple[torch.Tensor, torch.Tensor]]) -> list[tuple[torch.Tensor, float]]:
+        """pairs: (content, style) CPU tensors.  Returns (result image, final loss) per pair."""
+        results: list[tuple[torch.Tensor, float] | None] = [None] * len(pairs)
+        lanes = len(self.runners)
+        main = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(main)
+        for wave in range(0, len(pairs), lanes):
+            active = list(enumerate(range(wave, min(wave + lanes, len(pairs)))))
+            for lane, idx in active:
+                with torch.cuda.stream(self.streams[lane]):
+                    self.runners[lane]._load(*pairs[idx])  # noqa: SLF001
+            for _ in range(self.steps):
+                for lane, _idx in active:
+                    with torch.cuda.stream(self.streams[lane]):
+                        self.runners[lane]._fused.step()  # noqa: SLF001
+            for lane, _idx in active:
+                with torch.cuda.stream(self.streams[lane]):
+                    self.runners[lane]._finish_async()  # noqa: SLF001
+            for lane, idx in active:
+                results[idx] = self.runners[lane]._collect()  # noqa: SLF001
+        for st in self.streams:
+            main.wait_stream(st)
+        return results  # type: ignore[return-value]

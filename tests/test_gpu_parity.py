@@ -328,3 +328,31 @@ def test_job_runner_reuses_graph_and_matches_fresh_runs(cuda_device) -> None:  #
         assert torch.equal(img.to(cuda_device), x.detach())
         assert loss == hist["total_loss"][-1]
     assert runner._fused.graph is graph_obj  # noqa: SLF001
+
+
+def test_job_pool_lanes_match_sequential_runner(cuda_device) -> None:  # noqa: ANN001
+    """StyleJobPool replays the step graphs of two independent jobs interleaved on two streams:
+    every job's result must be bit-identical to the one-at-a-time StyleJobRunner's."""
+    import style_transfer_visualizer_b200.core_model as cm
+    from oracle import stv_oracle as orc
+    from style_transfer_visualizer_b200 import jobs
+
+    def fresh_model():  # noqa: ANN202
+        original = cm.initialize_vgg
+        cm.initialize_vgg = lambda: orc.vgg19_features(0)
+        try:
+            return cm.StyleContentModel([0, 5, 10, 19, 28], [21]).to(cuda_device)
+        finally:
+            cm.initialize_vgg = original
+
+    pairs = [(orc.synthetic_image(30 + 2 * j, 64, 96), orc.synthetic_image(31 + 2 * j, 64, 96))
+             for j in range(5)]
+    seq = jobs.StyleJobRunner(fresh_model(), 64, 96, steps=5, lr=0.01, device=cuda_device)
+    want = [seq.run_job(c, s) for c, s in pairs]
+    pool = jobs.StyleJobPool(fresh_model, 64, 96, steps=5, lanes=2, lr=0.01, device=cuda_device)
+    got = pool.run(pairs)
+    assert len(got) == len(want)
+    for (gi, gl), (wi, wl) in zip(got, want):
+        assert torch.equal(gi, wi)
+        assert gl == wl
+    assert sum(r.jobs_done for r in pool.runners) == 5
