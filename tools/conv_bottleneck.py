@@ -25,7 +25,7 @@ for (h, w, c, n, bn, mh, pair) in eval(os.environ["CFGS"]):
 '''
 cfgs = eval(sys.argv[1]) if len(sys.argv) > 1 else [(64, 64, 512, 512, 128, 1, 0), (64, 64, 512, 512, 128, 1, 1), (64, 64, 512, 512, 256, 1, 1),
                                                     (128, 128, 256, 256, 256, 1, 0), (128, 128, 256, 256, 256, 1, 1), (32, 32, 512, 512, 64, 1, 0)]
-for dbg in (0, 32, 15, 47, 7, 39):
+for dbg in (0, 1, 2, 3, 4, 7, 8, 12, 15):
     print(f"STV_CONV_DEBUG={dbg} (1 skip B loads, 2 skip A loads, 4 skip stores, 8 skip MMAs)", flush=True)
     env = dict(os.environ, STV_CONV_DEBUG=str(dbg), CFGS=repr(cfgs))
     subprocess.run([sys.executable, "-c", code], env=env, timeout=120, check=False)
