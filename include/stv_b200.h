@@ -52,6 +52,14 @@ int stv_conv3x3_first_fwd(const float* img_nchw, const float* w /*[64][3][3][3]*
  * would otherwise truncate it (a systematic shrink of the Gram entries). */
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
                     int Cout, float* out_pre, float* out_post, int round_pre, void* stream);
+/* The same followed by the MaxPool2d(2, 2) that VGG19 applies to conv1_2 / 2_2 / 3_4 / 4_4
+ * (core_model.py:134-135): out_pool [H/2][W/2][Cout] = 2x2 / stride-2 max of out_post, floor mode.
+ * The pool is computed in the conv epilogue from the accumulator tile (no re-read of out_post);
+ * results are identical to stv_conv3x3_fwd + stv_maxpool2_fwd.  out_post is still written: the
+ * pool backward needs it. */
+int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                         int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
+                         int round_pre, void* stream);
 
 /* ---- VGG conv stack: input gradient (autograd of the above; optimization.py:313) ---------- */
 /* dx = [relu_src > 0] .* conv_transpose(dy) (+ dx when accumulate != 0).

@@ -136,6 +136,22 @@ int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H
                             out_post, rf, nullptr, 0, 0, 0, S(stream));
 }
 
+int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                         int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
+                         int round_pre, void* stream) {
+  STV_REQUIRE(out_post != nullptr && out_pool != nullptr,
+              "stv_conv3x3_fwd_pool: out_post and out_pool are required");
+  const int rf = 2 | (round_pre ? 1 : 0);
+  if (use_conv_v1()) {
+    if (int rc = conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr,
+                                   out_pre, out_post, rf, 0, 0, 0, S(stream)))
+      return rc;
+    return maxpool2_fwd_launch(out_post, H, W, Cout, out_pool, S(stream));
+  }
+  return conv_igemm2_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
+                            out_post, rf, nullptr, 0, 0, 0, S(stream), out_pool);
+}
+
 int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                       const float* relu_src, int accumulate, float* dx, void* stream) {
   if (use_conv_v1())

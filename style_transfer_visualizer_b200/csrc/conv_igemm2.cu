@@ -49,6 +49,8 @@ struct Conv2Params {
   float* out_pre;
   float* out_post;
   int round_pre, round_post;
+  float* out_pool;     // optional fused 2x2 / stride-2 max pool of the post-ReLU output
+                       // ([H/2][W/2][N], floor mode); plain forward epilogue, tw in {8, 16} only
   float* out_nchw3;    // N == 16 variant: [3][H][W] planes
   int debug;           // STV_CONV_DEBUG bits (bottleneck experiments; results are then garbage):
                        // 1 skip weight loads, 2 skip activation loads, 4 skip stores, 8 skip MMAs
@@ -380,12 +382,22 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             // as eight 16-byte stores (the whole 128-byte line is produced back to back by one
             // thread, which L2 merges); cheaper than the transpose when nothing has to be read.
             const size_t row_off = (static_cast<size_t>(py) * p.W + px) * p.N + n0;
+            // Fused max pool: the 2x2 window of a pooled pixel lives in four lanes of this warp
+            // (x neighbour = lane ^ 1, y neighbour = lane ^ tw; tile origins are even), so two
+            // shuffles per value replace the separate pool kernel's re-read of `post`.  Max commutes
+            // with the monotonic tf32 rounding, so the result equals pooling the stored tensor.
+            const bool pool = p.out_pool != nullptr;
+            const int Ho = p.H >> 1, Wo = p.W >> 1;
+            const bool pool_writer = pool && !(py & 1) && !(px & 1) && (py >> 1) < Ho &&
+                                     (px >> 1) < Wo && !(p.debug & 4);
+            const size_t pool_off =
+                (static_cast<size_t>(py >> 1) * Wo + (px >> 1)) * p.N + n0;
 #pragma unroll 1
             for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
               uint32_t r[32];
               tmem_ld_32x32(trow + cb, r);
               tmem_ld_wait();
-              if (valid) {
+              if (valid || pool) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + cb + 4 * j);
@@ -395,7 +407,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   v.z = fmaf(__uint_as_float(r[4 * j + 2]), alpha, b.z);
                   v.w = fmaf(__uint_as_float(r[4 * j + 3]), alpha, b.w);
                   const int col = cb + 4 * j;
-                  if (p.out_pre) {
+                  if (p.out_pre && valid) {
                     float4 o = v;
                     if (p.round_pre) {
                       o.x = round_tf32(o.x); o.y = round_tf32(o.y);
@@ -411,7 +423,20 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                       o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                       o.z = round_tf32(o.z); o.w = round_tf32(o.w);
                     }
-                    *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                    if (valid) *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                    if (pool) {  // warp-uniform branch: every lane takes part in the shuffles
+                      float4 m = o;
+                      m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 1));
+                      m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, 1));
+                      m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, 1));
+                      m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 1));
+                      m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, p.tw));
+                      m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, p.tw));
+                      m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, p.tw));
+                      m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, p.tw));
+                      if (pool_writer)
+                        *reinterpret_cast<float4*>(p.out_pool + pool_off + col) = m;
+                    }
                   }
                 }
               }
@@ -623,6 +648,8 @@ static long count_tiles(int H, int W, int N, int mh, int tw, int bn) {
   return static_cast<long>((H + th - 1) / th) * ((W + tw - 1) / tw) * (N / bn);
 }
 
+static int g_want_pool = 0;  // the launch in progress asks for the fused pool: tw = 32 is excluded
+
 static int pick_tw(int H, int W, int mh) {
   // least padded pixels (= MMA work); the dy halo only inflates A traffic, so it is a tie-breaker
   const int tw_opts[3] = {16, 32, 8};
@@ -630,6 +657,7 @@ static int pick_tw(int H, int W, int mh) {
   double best_cost = -1.0;
   for (int i = 0; i < 3; ++i) {
     const int tw = tw_opts[i], th = 128 * mh / tw;
+    if (g_want_pool && tw == 32) continue;  // a 2x2 window must sit inside one epilogue warp
     const double area = static_cast<double>((H + th - 1) / th) * th * (((W + tw - 1) / tw) * tw);
     const double cost = area * (1.0 + 0.15 * 2.0 / th);
     if (best_cost < 0 || cost < best_cost) {
@@ -683,7 +711,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
                        const float* bias, const float* alpha, const float* mask_src,
                        const float* add_src, float* out_pre, float* out_post, int round_flags,
                        float* out_nchw3, int force_n, int force_mh, int force_tw,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, float* out_pool) {
   STV_REQUIRE(C % 32 == 0 && C >= 32, "conv_igemm2: input channels %d must be a multiple of 32", C);
   STV_REQUIRE(N % 64 == 0 || N == 16, "conv_igemm2: output channels %d must be 16 or a multiple of 64", N);
   STV_REQUIRE(taps == 9 || taps == 1, "conv_igemm2: taps must be 9 or 1 (got %d)", taps);
@@ -698,7 +726,18 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
     env_heavy = e ? atoi(e) : 1;
   }
   const int heavy = env_heavy && (mask_src != nullptr || add_src != nullptr);
+  static int env_fuse_pool = -1;
+  if (env_fuse_pool < 0) {
+    const char* e = getenv("STV_FUSE_POOL");
+    env_fuse_pool = (e && e[0] == '0') ? 0 : 1;
+  }
+  STV_REQUIRE(out_pool == nullptr || (out_post != nullptr && N != 16),
+              "conv_igemm2: the fused pool needs the post-ReLU output");
+  const bool pool_ok = out_pool != nullptr && env_fuse_pool && mask_src == nullptr &&
+                       add_src == nullptr && force_tw != 32;
+  g_want_pool = pool_ok ? 1 : 0;
   const TileChoice tc = choose_tiles(H, W, C, N, taps, heavy, force_n, force_mh, force_tw);
+  g_want_pool = 0;
   Conv2Params p;
   p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps;
   p.tw = tc.tw; p.th = tc.th;
@@ -713,6 +752,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   p.out_pre = out_pre; p.out_post = out_post;
   p.round_pre = round_flags & 1; p.round_post = (round_flags >> 1) & 1;
   p.out_nchw3 = out_nchw3;
+  p.out_pool = (pool_ok && tc.tw != 32) ? out_pool : nullptr;
   {
     const char* e = getenv("STV_CONV_DEBUG");
     p.debug = e ? atoi(e) : 0;
@@ -790,6 +830,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   int grid = work_ctas < sms * ctas_per_sm ? work_ctas : sms * ctas_per_sm;
   if (tc.pair) grid &= ~1;
 
+  auto dispatch = [&]() -> int {
 #define STV_L2(BN, MHV)                                                          \
   if (tc.block_n == BN && tc.mh == MHV && !tc.pair) {                            \
     if (p.tps == 3) return launch2<BN, MHV, 3, false>(tx, twm, p, grid, stream); \
@@ -818,6 +859,12 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
 #undef STV_L2
   set_error("conv_igemm2: no kernel for N tile %d / M halves %d", tc.block_n, tc.mh);
   return 2;
+  };
+  if (int rc = dispatch()) return rc;
+  // no fused pool for this shape (tw = 32 forced, or fusion disabled): separate pool kernel
+  if (out_pool != nullptr && p.out_pool == nullptr)
+    return maxpool2_fwd_launch(out_post, H, W, N, out_pool, stream);
+  return 0;
 }
 
 }  // namespace stv

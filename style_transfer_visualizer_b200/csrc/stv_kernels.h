@@ -18,7 +18,7 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
                        const float* bias, const float* alpha, const float* mask_src,
                        const float* add_src, float* out_pre, float* out_post, int round_flags,
                        float* out_nchw3, int force_n, int force_mh, int force_tw,
-                       cudaStream_t stream);
+                       cudaStream_t stream, float* out_pool = nullptr);
 
 // pair_mode -1: built-in rule table; 0: single-CTA tiles only; 1: CTA pairs (cta_group::2) wherever
 // legal.  a_stages / b_stages / tps > 0 override the ring depths and weight taps per stage.

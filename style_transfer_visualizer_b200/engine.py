@@ -233,11 +233,14 @@ class VggLossEngine:
                 ops.conv3x3_first_fwd(x, st.weight, st.bias, ws.pre[0], ws.post[0],
                                       round_pre=self._round_pre(st))
             else:
+                # the MaxPool2d after conv1_2 / 2_2 / 3_4 / 4_4 is computed in the conv epilogue
+                fused_pool = ws.pool[s] if st.pool_idx is not None and ws.post[s] is not None else None
                 ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s],
-                                round_pre=self._round_pre(st))
+                                round_pre=self._round_pre(st), out_pool=fused_pool)
             cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
             if st.pool_idx is not None:
-                ops.maxpool2_fwd(ws.post[s], ws.pool[s])
+                if s == 0 or ws.post[s] is None:
+                    ops.maxpool2_fwd(ws.post[s], ws.pool[s])
                 cur = ws.pool[s]
             if after_stage is not None:
                 after_stage(s, st)

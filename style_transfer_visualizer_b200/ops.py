@@ -44,10 +44,16 @@ def conv3x3_first_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | N
 
 def conv3x3_fwd(x: torch.Tensor, w_fwd: torch.Tensor, bias: torch.Tensor | None,
                 out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
-                round_pre: bool = False) -> None:
+                round_pre: bool = False, out_pool: torch.Tensor | None = None) -> None:
+    """3x3 conv + bias (+ReLU into out_post); with ``out_pool`` also the 2x2 max pool of out_post,
+    computed in the conv epilogue (``stv_conv3x3_fwd_pool``)."""
     _chk(x, "x")
     h, wd, cin = x.shape
     cout = w_fwd.shape[1]
+    if out_pool is not None:
+        nat.call("stv_conv3x3_fwd_pool", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
+                 nat.ptr(out_pre), nat.ptr(out_post), nat.ptr(out_pool), int(round_pre), _s(x))
+        return
     nat.call("stv_conv3x3_fwd", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
              nat.ptr(out_pre), nat.ptr(out_post), int(round_pre), _s(x))
 

@@ -365,6 +365,32 @@ def case_conv_variants() -> bool:
         ok &= report(f"style_bwd C={c} accumulate", rel_l2(out, ref), 2e-3)
         ops.style_bwd(xf, s, gw, out, accumulate=False)
         ok &= report(f"style_bwd C={c}", rel_l2(out, 1e5 * (xf.double() @ s.double()).float()), 2e-3)
+    # conv + fused 2x2 max pool (epilogue shuffles) vs conv followed by the pool kernel: identical
+    # bits, pre / post outputs untouched; even, odd and tiny sizes, every tile family incl. pairs
+    for (hh, ww, ci, co) in [(40, 56, 64, 64), (37, 53, 64, 128), (70, 94, 128, 128), (33, 47, 128, 256),
+                             (24, 40, 256, 256), (19, 8, 256, 512), (16, 16, 512, 512), (9, 11, 64, 64),
+                             (64, 24, 64, 64)]:
+        xx = torch.randn(hh, ww, ci, device=dev, generator=g)
+        wt2 = torch.randn(co, ci, 3, 3, device=dev, generator=g) * 0.05
+        wf2, _ = ops.pack_conv_weights(wt2)
+        b2 = torch.randn(co, device=dev, generator=g)
+        for pair_mode in (-1, 0, 1):
+            ops.conv_set_tuning(pair_mode)
+            pre_a = torch.full((hh, ww, co), float("nan"), device=dev)
+            post_a = torch.full((hh, ww, co), float("nan"), device=dev)
+            pool_a = torch.full((hh // 2, ww // 2, co), float("nan"), device=dev)
+            ops.conv3x3_fwd(xx, wf2, b2, pre_a, post_a, out_pool=pool_a)
+            pre_b = torch.empty_like(pre_a)
+            post_b = torch.empty_like(post_a)
+            pool_b = torch.empty_like(pool_a)
+            ops.conv3x3_fwd(xx, wf2, b2, pre_b, post_b)
+            ops.maxpool2_fwd(post_b, pool_b)
+            same = torch.equal(pre_a, pre_b) and torch.equal(post_a, post_b) and torch.equal(pool_a, pool_b)
+            ref_pool = F.max_pool2d(post_b.permute(2, 0, 1)[None], 2)[0].permute(1, 2, 0)
+            same = same and torch.equal(pool_a, ref_pool)
+            ok &= report(f"conv+fused pool {hh}x{ww} {ci}->{co} pair_mode={pair_mode}",
+                         0.0 if same else 1.0, 0.0)
+    ops.conv_set_tuning()
     torch.cuda.synchronize()
     return ok
 
