@@ -9,16 +9,23 @@
 //     used by the three dy taps through row-shifted UMMA descriptors.  With tw a multiple of 8
 //     every 8-row core-matrix group is one 1024-byte-aligned run of 8 pixels, so the shifted views
 //     keep the canonical K-major SWIZZLE_128B layout (SBO = 1024) -- A traffic drops 3x;
-//   * a CTA owns M = 256 pixels (two 128-row accumulators in TMEM) that share every weight stage
-//     -- B traffic per FLOP halves;
+//   * a CTA owns M = 128 or 256 pixels (one or two 128-row accumulators in TMEM) that share every
+//     weight stage;
+//   * ONE operand ring: stage s = {A patch, the three dy weight taps of that (slab, dx)} behind one
+//     full / empty mbarrier pair, so the single MMA-issuing thread pays one tcgen05.commit (a ~350
+//     cycle stall of that thread on this part) per 12-24 MMAs; 3-4 stages in flight cover the
+//     commit -> producer -> TMA -> consumer chain (~1.7 us) that re-arms a stage.  (A legacy mode
+//     with separate A / B rings and one tap per weight stage remains for forced configurations.)
 //   * the kernel is persistent (one CTA per SM, static tile schedule, n-tile-major so concurrent
-//     CTAs share weights in L2); operand rings keep streaming across tile boundaries and, when TMEM
+//     CTAs share weights in L2); the ring keeps streaming across tile boundaries and, when TMEM
 //     allows (2 * M_HALVES * BLOCK_N <= 512 columns), the accumulator is double-buffered so the
-//     epilogue of tile i overlaps the main loop of tile i+1.
+//     epilogue of tile i overlaps the main loop of tile i+1;
 //   * PAIR variant (cluster of 2 CTAs, tcgen05 cta_group::2): the two CTAs of a pair own two
 //     different pixel patches but the SAME output-channel tile; each stages only HALF of every
-//     weight stage (BLOCK_N/2 rows) and the leader's M = 256 MMAs read both halves.  Weight
-//     traffic per CTA -- the larger share of the L2->SM stream that bounds this kernel -- halves.
+//     weight tap (BLOCK_N/2 rows) and the leader's M = 256 MMAs read both halves.  Halving the
+//     weight bytes is what lets a three-tap stage and a 3-deep ring fit for 256-wide tiles;
+//   * epilogue options: bias / alpha, ReLU + tf32 rounding, dual pre / post outputs, fused 2x2 max
+//     pool (forward); ReLU gate + accumulate through a shared-memory transpose (dgrad, Gram backward).
 // Also hosts the N = 16 variant used for conv1_1's input gradient (64 -> 3 channels, written as
 // NCHW planes): the 3 real output channels are padded to the smallest legal UMMA N.
 #include <stdlib.h>
@@ -62,11 +69,6 @@ struct Conv2Params {
 // with anything, and on small feature maps every CTA has just one tile).
 #ifndef STV_EPI_WIDE
 #define STV_EPI_WIDE 1
-#endif
-// Issuing the first ring of (constant) weight stages BEFORE the programmatic-dependency wait was
-// measured neutral-to-negative (profiles/r1_conv_ab_epilogue_prefetch.log): off by default.
-#ifndef STV_PREFETCH_B
-#define STV_PREFETCH_B 0
 #endif
 __host__ __device__ constexpr int conv2_epi_warps(int block_n) {
   return (STV_EPI_WIDE && block_n >= 128) ? 8 : 4;
@@ -113,11 +115,6 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t stage_base =
       (bar_base + 8 * num_bars + 16 + static_cast<uint32_t>(p.N) * 4 + 127u) & ~127u;
 
-  const bool poll = (p.debug & 32) != 0;
-  auto WAIT = [poll](uint32_t bar, uint32_t parity) {
-    if (poll) mbar_wait_poll(bar, parity);
-    else mbar_wait(bar, parity);
-  };
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kc = p.C >> 5;
@@ -159,32 +156,9 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch, bias staging -- none of it touches activations) may overlap the tail of the previous
-  // kernel in the stream; so may the first ring of WEIGHT stages of a 3x3 conv (packed once, never
-  // rewritten; the 1x1 style-backward operand is produced inside the step and is not prefetched).
-  int b_pre = 0;
-  if (STV_PREFETCH_B && !p.uni && warp == 0 && lane == 0 && p.taps == 9 && !(p.debug & 1) &&
-      worker < p.tiles_total) {
-    const uint32_t b_full_c = PAIR ? mapa_u32(b_full, 0) : b_full;
-    const int n0 = (worker / p.tiles_m) * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
-    int c = 0, dxi = 0, dyi = 0;
-    for (; b_pre < BS && c < kc; ++b_pre) {
-      if constexpr (PAIR) mbar_expect_tx_cluster(b_full_c + 8 * b_pre, TPS * Cfg::kBBytes);
-      else mbar_expect_tx(b_full + 8 * b_pre, TPS * Cfg::kBBytes);
-#pragma unroll
-      for (int u = 0; u < TPS; ++u) {
-        const int tap = (dyi + u) * 3 + dxi;
-        if constexpr (PAIR)
-          tma_load_2d_pair(b_base + (b_pre * TPS + u) * Cfg::kBBytes, &tmap_w, b_full_c + 8 * b_pre,
-                           c << 5, tap * p.N + n0);
-        else
-          tma_load_2d(b_base + (b_pre * TPS + u) * Cfg::kBBytes, &tmap_w, b_full + 8 * b_pre,
-                      c << 5, tap * p.N + n0);
-      }
-      dyi += TPS;
-      if (dyi >= 3) { dyi = 0; if (++dxi == 3) { dxi = 0; ++c; } }
-    }
-  }
-  // From here on we read / write tensors the previous kernel may still be using.
+  // kernel in the stream; from here on we read / write tensors it may still be using.  (Issuing
+  // the first ring of weight stages before this wait was tried and measured neutral-to-negative,
+  // profiles/r1_conv_ab_epilogue_prefetch.log.)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -205,7 +179,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int n0 = nt * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
-            WAIT(a_empty + 8 * as, aph ^ 1);
+            mbar_wait(a_empty + 8 * as, aph ^ 1);
             const int cur = as;
             const uint32_t a_bytes = (p.debug & 2) ? 0u : static_cast<uint32_t>(p.a_stage_bytes);
             const uint32_t b_bytes = (p.debug & 1) ? 0u : static_cast<uint32_t>(TPS * Cfg::kBBytes);
@@ -232,12 +206,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               if (p.uni) {
                 slot = cur; bar_l = a_full + 8 * cur; bar_c = a_full_c + 8 * cur;
               } else {
-                if (b_pre > 0) {  // this stage was issued before the dependency wait
-                  --b_pre;
-                  if (++bs == BS) { bs = 0; bph ^= 1; }
-                  continue;
-                }
-                WAIT(b_empty + 8 * bs, bph ^ 1);
+                mbar_wait(b_empty + 8 * bs, bph ^ 1);
                 slot = bs; bar_l = b_full + 8 * bs; bar_c = b_full_c + 8 * bs;
                 if (++bs == BS) { bs = 0; bph ^= 1; }
                 if (b_bytes == 0) {
@@ -282,18 +251,18 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       for (int t = worker; t < p.tiles_total; t += workers) {
         // epilogue (of both CTAs) has drained this accumulator
         if constexpr (PAIR) mbar_wait_cluster(acc_empty + 8 * acc, accph ^ 1);
-        else WAIT(acc_empty + 8 * acc, accph ^ 1);
+        else mbar_wait(acc_empty + 8 * acc, accph ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * (MH * BLOCK_N);
         uint32_t accum = 0;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
-            WAIT(a_full + 8 * as, aph);
+            mbar_wait(a_full + 8 * as, aph);
             const uint32_t a_lo =
                 (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
-              if (!p.uni) WAIT(b_full + 8 * bs, bph);
-              if (!(p.debug & 16)) tc_fence_after();
+              if (!p.uni) mbar_wait(b_full + 8 * bs, bph);
+              tc_fence_after();
               const uint32_t b_slot = p.uni ? as : bs;
               const uint32_t b_lo =
                   (((b_base + b_slot * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
@@ -348,7 +317,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const int mt = PAIR ? 2 * (t - nt * p.tiles_m) + static_cast<int>(rank) : t - nt * p.tiles_m;
       const int ty0 = (mt / p.tiles_x) * p.th, tx0 = (mt % p.tiles_x) * p.tw;
       const int n0 = nt * BLOCK_N;
-      WAIT(acc_full + 8 * acc, accph);
+      mbar_wait(acc_full + 8 * acc, accph);
       tc_fence_after();
 #pragma unroll 1
       for (int hf = 0; hf < MH; ++hf) {

@@ -117,35 +117,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Pure polling variant (mbarrier.test_wait never suspends the thread).
-__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if ((++spins & 0xfff) == 0) {
-      uint64_t now = globaltimer_ns();
-      if (t0 == 0) {
-        t0 = now;
-      } else if (now - t0 > STV_WATCHDOG_NS) {
-        printf("stv: mbarrier watchdog fired (block %d thread %d bar 0x%x parity %u)\n",
-               blockIdx.x, threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-
 // --- TMA ------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
