@@ -151,6 +151,13 @@ int stv_lbfgs_step(float* x, const float* g, long n, int history, float* hist_s,
 int stv_frame_to_u8(const float* img_nchw, int H, int W, int denormalize, int rounding,
                     unsigned char* out_hwc, void* stream);
 
+/* ---- image load (image_io.py:64-84 apply_transforms: ToTensor + optional Normalize) --------- */
+/* img HWC uint8 (device) -> out NCHW fp32 [3][H][W]: x / 255, then (x - mean) / std when
+ * normalize != 0, in torchvision's operation order (bit-identical).  Lets the host ship the image
+ * as bytes: 4x less PCIe traffic than the reference's fp32 upload. */
+int stv_image_from_u8(const unsigned char* img_hwc, int H, int W, int normalize, float* out_nchw,
+                      void* stream);
+
 /* ---- misc --------------------------------------------------------------------------------- */
 int stv_nchw_to_nhwc(const float* src, int C, int H, int W, float* dst, void* stream);
 int stv_nhwc_to_nchw(const float* src, int C, int H, int W, float* dst, void* stream);

@@ -54,6 +54,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_lbfgs_workspace_floats": [_l, _i],
     "stv_lbfgs_step": [_vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp],
     "stv_frame_to_u8": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "stv_image_from_u8": [_vp, _i, _i, _i, _vp, _vp],
     "stv_nchw_to_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "stv_nhwc_to_nchw": [_vp, _i, _i, _i, _vp, _vp],
     "stv_finite_flags": [_vp, _i, _vp, _vp],

@@ -277,6 +277,12 @@ int stv_frame_to_u8(const float* img_nchw, int H, int W, int denormalize, int ro
                     unsigned char* out_hwc, void* stream) {
   return frame_to_u8_launch(img_nchw, H, W, denormalize, rounding, out_hwc, S(stream));
 }
+int stv_image_from_u8(const unsigned char* img_hwc, int H, int W, int normalize, float* out_nchw,
+                      void* stream) {
+  STV_REQUIRE(H > 0 && W > 0 && img_hwc != nullptr && out_nchw != nullptr,
+              "stv_image_from_u8: empty image or null buffer");
+  return image_from_u8_launch(img_hwc, H, W, normalize, out_nchw, S(stream));
+}
 int stv_nchw_to_nhwc(const float* src, int C, int H, int W, float* dst, void* stream) {
   return nchw_to_nhwc_launch(src, C, H, W, dst, S(stream));
 }

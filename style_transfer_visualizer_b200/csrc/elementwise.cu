@@ -411,6 +411,27 @@ frame_to_u8_kernel(const float* __restrict__ img, long hw, int denorm, int round
 }
 
 // ------------------------------------------------------------------------------------------
+// image load: HWC uint8 -> NCHW fp32, ToTensor (x / 255) then optional Normalize ((x - mean) / std),
+// the same IEEE operations in the same order as torchvision, so the result is bit-identical.
+// One thread = one pixel (3 bytes in, 3 planes out).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+image_from_u8_kernel(const unsigned char* __restrict__ hwc, long hw, int normalize,
+                     float* __restrict__ out) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long p = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; p < hw;
+       p += static_cast<long>(gridDim.x) * 256) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = __fdiv_rn(static_cast<float>(hwc[p * 3 + ch]), 255.0f);
+      if (normalize) v = __fdiv_rn(__fsub_rn(v, mean[ch]), stdv[ch]);
+      out[ch * hw + p] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // layout conversion (API boundary: the reference exposes NCHW tensors) and finiteness flags
 // ------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, long hw,
@@ -568,6 +589,14 @@ int frame_to_u8_launch(const float* img_nchw, int H, int W, int denormalize, int
   const long hw = static_cast<long>(H) * W;
   frame_to_u8_kernel<<<grid_for((hw + 3) / 4, 256, stream_blocks()), 256, 0, stream>>>(
       img_nchw, hw, denormalize, rounding, out_hwc);
+  STV_LAUNCH_CHECK();
+  return 0;
+}
+int image_from_u8_launch(const unsigned char* hwc, int H, int W, int normalize, float* out_nchw,
+                         cudaStream_t stream) {
+  const long hw = static_cast<long>(H) * W;
+  image_from_u8_kernel<<<grid_for(hw, 256, stream_blocks()), 256, 0, stream>>>(hwc, hw, normalize,
+                                                                               out_nchw);
   STV_LAUNCH_CHECK();
   return 0;
 }

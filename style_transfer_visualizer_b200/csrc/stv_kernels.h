@@ -75,6 +75,8 @@ int lbfgs_step_launch(float* x, const float* g, long n, int m, float* hist_s, fl
                       float tol_change, cudaStream_t stream);
 int frame_to_u8_launch(const float* img_nchw, int H, int W, int denormalize, int rounding,
                        unsigned char* out_hwc, cudaStream_t stream);
+int image_from_u8_launch(const unsigned char* hwc, int H, int W, int normalize, float* out_nchw,
+                         cudaStream_t stream);
 int nchw_to_nhwc_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);
 int nhwc_to_nchw_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);
 int finite_flags_launch(const float* vals, int n, int* flags, cudaStream_t stream);

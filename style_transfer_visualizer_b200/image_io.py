@@ -1,4 +1,11 @@
-"""Output-side image helpers of the hot path: de-normalisation and the timelapse frame readback.
+"""Image helpers either side of the hot path: load + preprocess, de-normalisation and the
+timelapse frame readback.
+
+``load_image`` / ``validate_image_dimensions`` / ``apply_transforms`` / ``load_image_to_tensor``
+keep the reference's names, errors and results (image_io.py:24-115).  On a CUDA device the image
+crosses PCIe as BYTES (pinned uint8 staging, non-blocking copy) and ONE kernel does ToTensor +
+Normalize there -- the same IEEE operations in torchvision's order, so the tensor is bit-identical
+to the reference's fp32 upload at a quarter of the transfer.
 
 ``denormalize`` / ``prepare_image_for_output`` keep the reference's semantics (image_io.py:118-152).
 ``FrameReadback`` replaces the reference's synchronous ``.cpu().numpy() * 255 -> astype(uint8)``
@@ -15,7 +22,55 @@ import numpy as np
 import torch
 
 from . import ops
-from .constants import DENORM_VIEW_SHAPE, IMAGENET_MEAN, IMAGENET_STD
+from .constants import (DENORM_VIEW_SHAPE, IMAGENET_MEAN, IMAGENET_STD, MAX_DIMENSION,
+                        MIN_DIMENSION)
+from .logging_utils import logger
+
+
+def load_image(path: str):  # noqa: ANN201
+    """PIL image in RGB mode (reference image_io.py:24-46)."""
+    from PIL import Image
+
+    try:
+        return Image.open(path).convert("RGB")
+    except FileNotFoundError as exc:
+        msg = f"Image file not found: '{path}'"
+        raise FileNotFoundError(msg) from exc
+    except OSError as exc:
+        msg = f"Error loading image '{path}': {exc!s}"
+        raise OSError(msg) from exc
+
+
+def validate_image_dimensions(img) -> None:  # noqa: ANN001
+    """Reject images below the minimum size, warn above the maximum (reference image_io.py:49-62)."""
+    if img.width < MIN_DIMENSION or img.height < MIN_DIMENSION:
+        msg = (f"Image too small: {img.width}x{img.height}. "
+               f"Minimum dimension is {MIN_DIMENSION}px.")
+        raise ValueError(msg)
+    if img.width > MAX_DIMENSION or img.height > MAX_DIMENSION:
+        logger.warning("Image is large: %dx%d. This may slow processing.", img.width, img.height)
+
+
+def apply_transforms(img, device: torch.device, *, normalize: bool) -> torch.Tensor:  # noqa: ANN001
+    """``ToTensor`` (+ ``Normalize``) of a PIL image -> ``[1, 3, H, W]`` fp32 on ``device``
+    (reference image_io.py:64-84)."""
+    arr = torch.from_numpy(np.asarray(img.convert("RGB"), dtype=np.uint8).copy())   # [H, W, 3] u8
+    if device.type == "cuda":
+        staged = arr.pin_memory().to(device, non_blocking=True)
+        return ops.image_from_u8(staged, normalize=normalize)
+    chw = arr.permute(2, 0, 1).contiguous().to(torch.float32).div(255)             # ToTensor
+    if normalize:
+        mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
+        std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
+        chw = chw.sub_(mean).div_(std)                                             # Normalize
+    return chw.unsqueeze(0).to(device)
+
+
+def load_image_to_tensor(path: str, device: torch.device, *, normalize: bool = False) -> torch.Tensor:
+    """Load, validate and preprocess an image as-is, no resizing (reference image_io.py:87-115)."""
+    img = load_image(path)
+    validate_image_dimensions(img)
+    return apply_transforms(img, device, normalize=normalize)
 
 
 def denormalize(tensor: torch.Tensor) -> torch.Tensor:

@@ -12,14 +12,12 @@ import random
 from dataclasses import dataclass
 from pathlib import Path
 
-import numpy as np
 import torch
 
 from . import core_model as stv_core_model
 from . import optimization as stv_optimizer
 from .config import StyleTransferConfig
-from .constants import IMAGENET_MEAN, IMAGENET_STD, MAX_DIMENSION, MIN_DIMENSION
-from .image_io import frame_to_numpy
+from .image_io import frame_to_numpy, load_image_to_tensor
 from .logging_utils import logger
 from .video import VideoFrameSink
 
@@ -50,34 +48,6 @@ def setup_device(device_name: str) -> torch.device:
     device = torch.device(device_name)
     logger.info("Using device: %s", device)
     return device
-
-
-def load_image_to_tensor(path: str, device: torch.device, *, normalize: bool = False) -> torch.Tensor:
-    """PIL RGB -> float [1,3,H,W] in [0,1] (-> ImageNet-normalised) on ``device`` (reference
-    image_io.py:87-115; pinned staging + non-blocking H2D)."""
-    from PIL import Image
-
-    try:
-        img = Image.open(path).convert("RGB")
-    except FileNotFoundError as exc:
-        msg = f"Image file not found: '{path}'"
-        raise FileNotFoundError(msg) from exc
-    if img.width < MIN_DIMENSION or img.height < MIN_DIMENSION:
-        msg = (f"Image too small: {img.width}x{img.height}. "
-               f"Minimum dimension is {MIN_DIMENSION}px.")
-        raise ValueError(msg)
-    if img.width > MAX_DIMENSION or img.height > MAX_DIMENSION:
-        logger.warning("Image is large: %dx%d. This may slow processing.", img.width, img.height)
-    arr = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy())            # [H, W, 3] u8
-    chw = arr.permute(2, 0, 1).contiguous().to(torch.float32).div(255)        # ToTensor semantics
-    if normalize:
-        mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
-        std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
-        chw = (chw - mean) / std
-    host = chw.unsqueeze(0)
-    if device.type == "cuda":
-        host = host.pin_memory()
-    return host.to(device, non_blocking=True)
 
 
 def style_transfer(paths: InputPaths, config: StyleTransferConfig, *,

@@ -296,3 +296,15 @@ def conv_set_tuning(pair_mode: int = -1, a_stages: int = 0, b_stages: int = 0, t
 def conv_set_pair_mode(mode: int) -> None:
     """-1: built-in rule table, 0: single-CTA conv tiles only, 1: CTA pairs wherever legal."""
     conv_set_tuning(mode)
+
+
+def image_from_u8(img_hwc: torch.Tensor, *, normalize: bool) -> torch.Tensor:
+    """uint8 ``[H, W, 3]`` on the device -> fp32 ``[1, 3, H, W]`` (ToTensor + optional Normalize)."""
+    if img_hwc.dtype != torch.uint8 or img_hwc.dim() != 3 or img_hwc.shape[2] != 3 \
+            or not img_hwc.is_contiguous():
+        msg = "image_from_u8 expects a contiguous uint8 [H, W, 3] tensor"
+        raise ValueError(msg)
+    h, w, _ = img_hwc.shape
+    out = torch.empty(1, 3, h, w, device=img_hwc.device, dtype=torch.float32)
+    nat.call("stv_image_from_u8", nat.ptr(img_hwc), h, w, int(normalize), nat.ptr(out), _s(img_hwc))
+    return out

@@ -356,3 +356,29 @@ def test_job_pool_lanes_match_sequential_runner(cuda_device) -> None:  # noqa: A
         assert torch.equal(gi, wi)
         assert gl == wl
     assert sum(r.jobs_done for r in pool.runners) == 5
+
+
+def test_image_load_kernel_is_bit_identical_to_torchvision(cuda_device, tmp_path) -> None:  # noqa: ANN001
+    """apply_transforms on the GPU ships bytes and normalises in one kernel: same bits as the
+    reference's torchvision ToTensor + Normalize followed by .to(device) (image_io.py:64-84)."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+
+    from style_transfer_visualizer_b200 import image_io
+    from style_transfer_visualizer_b200.constants import IMAGENET_MEAN, IMAGENET_STD
+
+    rng = np.random.default_rng(3)
+    for h, w in [(64, 64), (70, 94), (129, 257)]:
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        arr[0, :256 if w >= 256 else w, 0] = np.arange(min(w, 256), dtype=np.uint8)  # every byte value
+        path = tmp_path / f"img_{h}x{w}.png"
+        Image.fromarray(arr).save(path)
+        for normalize in (False, True):
+            got = image_io.load_image_to_tensor(str(path), cuda_device, normalize=normalize)
+            pipeline = [transforms.ToTensor()]
+            if normalize:
+                pipeline.append(transforms.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD))
+            want = transforms.Compose(pipeline)(Image.open(path).convert("RGB")).unsqueeze(0)
+            assert got.device.type == "cuda" and got.shape == want.shape
+            assert torch.equal(got.cpu(), want)

@@ -350,3 +350,50 @@ def test_history_is_bounded(caplog: pytest.LogCaptureFixture) -> None:
                                 progress_bar=Bar())
     _, hist, _ = runner.run()
     assert len(hist["total_loss"]) == 2048
+
+
+def test_image_load_path_matches_reference_semantics(tmp_path, caplog) -> None:  # noqa: ANN001
+    """reference image_io.py:24-115 -- names, errors, warning and (on CPU) the exact tensor that
+    torchvision's ToTensor + Normalize produce."""
+    import logging
+
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+
+    from style_transfer_visualizer_b200 import image_io
+    from style_transfer_visualizer_b200.constants import IMAGENET_MEAN, IMAGENET_STD
+
+    with pytest.raises(FileNotFoundError, match="Image file not found: "):
+        image_io.load_image(str(tmp_path / "missing.png"))
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not an image")
+    with pytest.raises(OSError, match="Error loading image"):
+        image_io.load_image(str(bad))
+    rng = np.random.default_rng(0)
+    small = tmp_path / "small.png"
+    Image.fromarray(rng.integers(0, 256, (32, 80, 3), dtype=np.uint8)).save(small)
+    with pytest.raises(ValueError, match=r"Image too small: 80x32\. Minimum dimension is 64px\."):
+        image_io.load_image_to_tensor(str(small), torch.device("cpu"))
+    ok = tmp_path / "ok.png"
+    arr = rng.integers(0, 256, (70, 94, 3), dtype=np.uint8)
+    Image.fromarray(arr).save(ok)
+    cpu = torch.device("cpu")
+    for normalize in (False, True):
+        got = image_io.load_image_to_tensor(str(ok), cpu, normalize=normalize)
+        pipeline = [transforms.ToTensor()]
+        if normalize:
+            pipeline.append(transforms.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD))
+        want = transforms.Compose(pipeline)(Image.open(ok).convert("RGB")).unsqueeze(0)
+        assert got.shape == (1, 3, 70, 94) and got.dtype == torch.float32
+        assert torch.equal(got, want)
+    grey = tmp_path / "grey.png"
+    Image.fromarray(arr[..., 0]).save(grey)   # converted to RGB on load
+    assert image_io.load_image(str(grey)).mode == "RGB"
+
+    class Big:
+        width, height = 4000, 100
+
+    caplog.set_level(logging.WARNING)
+    image_io.validate_image_dimensions(Big())
+    assert any("Image is large: 4000x100" in r.getMessage() for r in caplog.records)
