@@ -397,3 +397,63 @@ def test_image_load_path_matches_reference_semantics(tmp_path, caplog) -> None: 
     caplog.set_level(logging.WARNING)
     image_io.validate_image_dimensions(Big())
     assert any("Image is large: 4000x100" in r.getMessage() for r in caplog.records)
+
+
+def test_runner_gif_collector_and_postfix(caplog) -> None:  # noqa: ANN001
+    """reference tests/test_optimization.py:394-441 (GIF frames mirror the video frames, the intro
+    crossfade goes to the GIF only when gif_include_intro), :1165-1223 (postfix from the latest
+    logged metrics), :725-742 (no summary line when nothing ran)."""
+    import logging
+
+    x = _img()
+    video, gif, bar = Sink(), Sink(), Bar()
+    cfg = _cfg(steps=4, save_every=2, log_every=2)
+    cfg.video.gif_include_intro = True
+    intro = np.zeros((8, 8, 3), dtype=np.uint8)
+    runner = OptimizationRunner(TinyModel(), x, cfg, optimizer=torch.optim.Adam([x], lr=0.1),
+                                progress_bar=bar, video_writer=video, gif_collector=gif,
+                                intro_last_frame=intro, intro_crossfade_frames=3)
+    runner.run()
+    # two timelapse frames each; the crossfade (3 blended frames) precedes the first one in both
+    assert len(video.frames) == 3 + 2 and len(gif.frames) == 3 + 2
+    assert np.array_equal(video.frames[-1], gif.frames[-1])
+    assert runner.intro_transition_done and runner.intro_last_frame is None
+    assert bar.postfix and set(bar.postfix[-1]) == {"style", "content", "loss"}
+    assert all(isinstance(v, str) for v in bar.postfix[-1].values())
+
+    x2 = _img()
+    gif2 = Sink()
+    cfg2 = _cfg(steps=2, save_every=1)
+    cfg2.video.gif_include_intro = False
+    OptimizationRunner(TinyModel(), x2, cfg2, optimizer=torch.optim.Adam([x2], lr=0.1),
+                       progress_bar=Bar(), gif_collector=gif2, intro_last_frame=intro,
+                       intro_crossfade_frames=3).run()
+    assert len(gif2.frames) == 2  # no crossfade in the GIF
+
+    caplog.set_level(logging.INFO)
+    caplog.clear()
+    x3 = _img()
+    idle = OptimizationRunner(TinyModel(), x3, _cfg(steps=2), optimizer=torch.optim.Adam([x3]),
+                              progress_bar=Bar())
+    idle._log_optimization_summary()  # noqa: SLF001
+    assert not any("Optimization finished" in r.getMessage() for r in caplog.records)
+
+
+def test_closure_reads_no_scalars_between_flushes(monkeypatch) -> None:  # noqa: ANN001
+    """reference tests/test_optimization.py:943-970: between log_every flushes the closure must not
+    pull scalars to the host (`.item()` is a device sync on CUDA)."""
+    calls = {"n": 0}
+    orig = torch.Tensor.item
+
+    def counting_item(self):  # noqa: ANN001, ANN202
+        calls["n"] += 1
+        return orig(self)
+
+    x = _img()
+    runner = OptimizationRunner(TinyModel(), x, _cfg(steps=9, log_every=5, save_every=100),
+                                optimizer=torch.optim.SGD([x], lr=0.01), progress_bar=Bar())
+    monkeypatch.setattr(torch.Tensor, "item", counting_item)
+    runner.run()
+    monkeypatch.undo()
+    # one flush at step 5 (three scalars) -- nothing at steps 1-4 and 6-9
+    assert calls["n"] <= 3
