@@ -13,7 +13,8 @@
 //     weight stage;
 //   * ONE operand ring: stage s = {A patch, the three dy weight taps of that (slab, dx)} behind one
 //     full / empty mbarrier pair, so the single MMA-issuing thread pays one tcgen05.commit (a ~350
-//     cycle stall of that thread on this part) per 12-24 MMAs; 3-4 stages in flight cover the
+//     cycle stall of that thread on this part) per 12-24 MMAs -- two-half tiles have one issuing
+//     thread per half, so one thread's stall hides behind the other's MMAs; 3-4 stages in flight cover the
 //     commit -> producer -> TMA -> consumer chain (~1.7 us) that re-arms a stage.  (A legacy mode
 //     with separate A / B rings and one tap per weight stage remains for forced configurations.)
 //   * the kernel is persistent (one CTA per SM, static tile schedule, n-tile-major so concurrent
@@ -73,7 +74,14 @@ struct Conv2Params {
 __host__ __device__ constexpr int conv2_epi_warps(int block_n) {
   return (STV_EPI_WIDE && block_n >= 128) ? 8 : 4;
 }
-__host__ __device__ constexpr int conv2_threads(int block_n) { return 64 + 32 * conv2_epi_warps(block_n); }
+// Two-half tiles get one MMA-issuing thread PER HALF (its own accumulator, so no ordering between
+// them): tcgen05.commit stalls its thread for ~500 cycles, which starves the tensor pipe when a
+// stage is only 12-24 short (N <= 128) MMAs; the other issuer's MMAs fill that hole
+// (profiles/r1_umma_peak.log: N=64 72 -> 53 cycles per MMA, N=128 87 -> 66).
+__host__ __device__ constexpr int conv2_issuers(int mh) { return mh == 2 ? 2 : 1; }
+__host__ __device__ constexpr int conv2_threads(int block_n, int mh) {
+  return 32 * (1 + conv2_issuers(mh) + conv2_epi_warps(block_n));
+}
 
 template <int BLOCK_N, int MH, bool PAIR>
 struct Conv2Cfg {
@@ -85,12 +93,14 @@ struct Conv2Cfg {
 };
 
 template <int BLOCK_N, int MH, int TPS, bool PAIR>
-__global__ void __launch_bounds__(conv2_threads(BLOCK_N), 1)
+__global__ void __launch_bounds__(conv2_threads(BLOCK_N, MH), 1)
 conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                         const __grid_constant__ CUtensorMap tmap_w, const Conv2Params p) {
   using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR>;
   constexpr int EW = conv2_epi_warps(BLOCK_N);
-  constexpr int kThreads2 = conv2_threads(BLOCK_N);
+  constexpr int NI = conv2_issuers(MH);
+  constexpr int kThreads2 = conv2_threads(BLOCK_N, MH);
+  constexpr int kFirstEpiWarp = 1 + NI;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // tile schedule: a "worker" is a CTA, or a CTA pair
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -128,10 +138,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // PAIR: the leader's "full" barriers collect one expect_tx arrival from each CTA's producer,
     // its "accumulator drained" barriers one arrival from each epilogue warp of both CTAs
     const uint32_t np = PAIR ? 2u : 1u;
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, np); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, np); mbar_init(b_empty + 8 * s, 1); }
+    // every issuer commits each stage / accumulator it has used
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, np); mbar_init(a_empty + 8 * s, NI); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, np); mbar_init(b_empty + 8 * s, NI); }
     for (int s = 0; s < kAcc; ++s) {
-      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_full + 8 * s, NI);
       mbar_init(acc_empty + 8 * s, EW * np);
     }
     fence_mbar_init();
@@ -145,8 +156,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       tmem_relinquish();
     }
   }
-  if (warp >= 2 && BLOCK_N != 16) {
-    for (int i = threadIdx.x - 64; i < p.N; i += kThreads2 - 64)
+  if (warp >= kFirstEpiWarp && BLOCK_N != 16) {
+    for (int i = threadIdx.x - 32 * kFirstEpiWarp; i < p.N; i += kThreads2 - 32 * kFirstEpiWarp)
       sbias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
@@ -234,8 +245,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer -----------------------------------------------
+  } else if (warp < kFirstEpiWarp) {
+    // ------------------------------ MMA issuer(s) --------------------------------------------
+    // issuer `me` owns the 128-pixel halves hf0 .. hf1-1 of every tile (all of them when NI == 1)
+    const int me = warp - 1;
+    const int hf0 = NI == 2 ? me : 0, hf1 = NI == 2 ? me + 1 : MH;
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(PAIR ? 256 : 128, BLOCK_N, 0, 0);
       // Descriptors: the upper word (SBO = 1024, version, SWIZZLE_128B) is constant; the lower word
@@ -269,7 +283,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
               for (int u = 0; u < TPS; ++u) {
 #pragma unroll
-                for (int hf = 0; hf < MH; ++hf) {
+                for (int hf = hf0; hf < hf1; ++hf) {
                   const uint32_t av = a_lo + (dyi + u) * row16 + hf * half16;
                   const uint32_t bv = b_lo + u * (Cfg::kBBytes >> 4);
 #pragma unroll
@@ -307,7 +321,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------ epilogue -------------------------------------------------
     const int q = warp & 3;
     constexpr int kCols = BLOCK_N / (EW / 4);      // columns drained by this warp
-    const int cb0 = ((warp - 2) >> 2) * kCols;
+    const int cb0 = ((warp - kFirstEpiWarp) >> 2) * kCols;
     int acc = 0;
     uint32_t accph = 0;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
@@ -416,7 +430,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
           // global memory would touch 32 different 128-byte lines per instruction, 16 bytes each;
           // the tile is transposed through shared memory instead so that 8 lanes cover one
           // pixel's 128 bytes: every global load/store instruction moves 4 complete lines.
-          const uint32_t stg = stage_base + (warp - 2) * 4096;
+          const uint32_t stg = stage_base + (warp - kFirstEpiWarp) * 4096;
           const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll 1
           for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
@@ -557,7 +571,7 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(conv2_threads(BLOCK_N));
+  cfg.blockDim = dim3(conv2_threads(BLOCK_N, MH));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
