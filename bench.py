@@ -205,11 +205,14 @@ def profile_dominant_kernel(model, x, steps: int) -> dict:  # noqa: ANN001
     from style_transfer_visualizer_b200 import _native as nat
 
     def conv_flops(name: str, a: tuple) -> float | None:
-        if name == "stv_conv3x3_fwd":      # (x, w, bias, H, W, Cin, Cout, ...)
+        if name in ("stv_conv3x3_fwd", "stv_conv3x3_fwd_bits", "stv_conv3x3_fwd_pool",
+                    "stv_conv3x3_fwd_pool_code"):       # (x, w, bias, H, W, Cin, Cout, ...)
             return 2.0 * 9 * a[3] * a[4] * a[5] * a[6]
-        if name == "stv_conv3x3_dgrad":    # (dy, w, H, W, Cout, Cin, ...)
-            return 2.0 * 9 * a[2] * a[3] * a[4] * a[5]
-        if name == "stv_style_bwd":        # (x, s, hw, C, ...)
+        if name in ("stv_conv3x3_dgrad", "stv_conv3x3_dgrad_bits", "stv_conv3x3_dgrad_unpool"):
+            return 2.0 * 9 * a[2] * a[3] * a[4] * a[5]  # (dy, w, H, W, Cout, Cin, ...)
+        if name == "stv_conv3x3_first_dgrad_tc":        # (dy, w16, H, W, Cout, ...): 3 real channels
+            return 2.0 * 9 * a[2] * a[3] * a[4] * 3
+        if name == "stv_style_bwd":                     # (x, s, hw, C, ...)
             return 2.0 * a[2] * a[3] * a[3]
         return None
 
@@ -615,12 +618,18 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compact-backward", type=int, default=1,
+                    help="0 = fp32 re-reads for the ReLU / pool backward (A/B against the bit codes)")
     ap.add_argument("--lanes", type=int, default=2,
                     help="jobs64 workload: independent jobs in flight per GPU (own stream + graph)")
     ap.add_argument("--sharded-graph", type=int, default=1,
                     help="4k workload: replay the sharded step from a CUDA graph (0 = eager)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if not args.compact_backward:
+        import style_transfer_visualizer_b200.engine as _eng
+
+        _eng.DEFAULT_COMPACT_BACKWARD = False
     if args.steps is None:
         args.steps = wl["steps"]
     if args.impl == "reference":

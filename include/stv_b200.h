@@ -21,12 +21,13 @@
 #define STV_B200_H_
 
 #include <stddef.h>
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define STV_ABI_VERSION 2
+#define STV_ABI_VERSION 3
 
 const char* stv_last_error(void);
 int stv_abi_version(void);
@@ -45,6 +46,13 @@ int stv_pack_conv_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout
 int stv_conv3x3_first_fwd(const float* img_nchw, const float* w /*[64][3][3][3]*/,
                           const float* bias, int H, int W, int Cout, float* out_pre,
                           float* out_post, int round_pre, void* stream);
+/* Same, also recording what autograd's ReLU backward needs (nn.ReLU, core_model.py:134-135):
+ * out_bits [H][W][Cout/32] words, bit (c % 32) of word c / 32 = (out_post[y][x][c] > 0).  The
+ * dgrad of the next layer gates with these bits (stv_conv3x3_dgrad_bits) instead of re-reading the
+ * fp32 activation: 1/32 of the bytes. */
+int stv_conv3x3_first_fwd_bits(const float* img_nchw, const float* w, const float* bias, int H,
+                               int W, int Cout, float* out_pre, float* out_post,
+                               unsigned* out_bits, int round_pre, void* stream);
 /* 3x3 pad-1 conv on the tensor cores (tcgen05, TF32 multiply, FP32 accumulate).
  * x: NHWC [H][W][Cin], w_fwd from stv_pack_conv_weights, Cin % 32 == 0, Cout % 64 == 0.
  * out_post is always stored rounded to TF32 (it is the next conv's MMA operand); round_pre != 0
@@ -52,6 +60,10 @@ int stv_conv3x3_first_fwd(const float* img_nchw, const float* w /*[64][3][3][3]*
  * would otherwise truncate it (a systematic shrink of the Gram entries). */
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
                     int Cout, float* out_pre, float* out_post, int round_pre, void* stream);
+/* Same + out_bits (see stv_conv3x3_first_fwd_bits). */
+int stv_conv3x3_fwd_bits(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                         int Cin, int Cout, float* out_pre, float* out_post, unsigned* out_bits,
+                         int round_pre, void* stream);
 /* The same followed by the MaxPool2d(2, 2) that VGG19 applies to conv1_2 / 2_2 / 3_4 / 4_4
  * (core_model.py:134-135): out_pool [H/2][W/2][Cout] = 2x2 / stride-2 max of out_post, floor mode.
  * The pool is computed in the conv epilogue from the accumulator tile (no re-read of out_post);
@@ -60,6 +72,15 @@ int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H
 int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, int H, int W,
                          int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
                          int round_pre, void* stream);
+/* Same, also recording what autograd's max_pool2d + ReLU backward need: out_code
+ * [H/2][W/2][Cout/8] words, one nibble per channel (channel c in bits 4*(c%8) of word c/8): bits 0-1
+ * = position (2*dy + dx) of the FIRST maximum of the 2x2 window in ATen's scan order, bit 2 = the
+ * pooled value is > 0 (ReLU gate).  With the codes the full-resolution activation has no reader
+ * left in the backward pass: out_post may be NULL (saves its write), and
+ * stv_conv3x3_dgrad_unpool routes the gradient without a pool-backward kernel. */
+int stv_conv3x3_fwd_pool_code(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                              int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
+                              unsigned* out_code, int round_pre, void* stream);
 
 /* ---- VGG conv stack: input gradient (autograd of the above; optimization.py:313) ---------- */
 /* dx = [relu_src > 0] .* conv_transpose(dy) (+ dx when accumulate != 0).
@@ -67,6 +88,18 @@ int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, 
  * w_dgrad from stv_pack_conv_weights.  Cout % 32 == 0, Cin % 64 == 0. */
 int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                       const float* relu_src, int accumulate, float* dx, void* stream);
+/* Same with the ReLU gate given as sign bits (out_bits of the forward conv that produced the
+ * gated activation; [H][W][Cin/32]); relu_bits may be NULL (no gating). */
+int stv_conv3x3_dgrad_bits(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                           const unsigned* relu_bits, int accumulate, float* dx, void* stream);
+/* dgrad of the conv that FOLLOWS a MaxPool2d(2, 2), fused with the pool's (and the preceding
+ * ReLU's) backward: dy [H][W][Cout] at pooled resolution, pool_code from
+ * stv_conv3x3_fwd_pool_code ([H][W][Cin/8]), dx [H2][W2][Cin] at the resolution before the pool
+ * (H = H2/2, W = W2/2, floor).  Every pooled gradient value is written to the recorded argmax
+ * position of its window (zero elsewhere, zero everywhere when the gate bit is clear).  A last row /
+ * column of dx dropped by floor mode is NOT written: allocate dx zero-filled. */
+int stv_conv3x3_dgrad_unpool(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                             const unsigned* pool_code, int H2, int W2, float* dx, void* stream);
 /* conv1_1 input gradient: dy NHWC [H][W][64] -> dimg NCHW [3][H][W] (this is input_img.grad). */
 int stv_conv3x3_first_dgrad(const float* dy, const float* w /*[64][3][3][3]*/, int H, int W,
                             int Cout, float* dimg_nchw, void* stream);
@@ -163,22 +196,25 @@ int stv_nchw_to_nhwc(const float* src, int C, int H, int W, float* dst, void* st
 int stv_nhwc_to_nchw(const float* src, int C, int H, int W, float* dst, void* stream);
 /* flags[i] |= !isfinite(vals[i]), i < n <= 32 (optimization.py:375-391, checked lazily). */
 int stv_finite_flags(const float* vals, int n, int* flags, void* stream);
+/* End of one optimisation step, graph-capturable (optimization.py:298-312 weighted total, :375-391
+ * finiteness checks, :402-422 loss recording): scores3 = {sum of the n_style style losses, sum of
+ * the n_content content losses, style_w * style + content_w * content}.  When counter != NULL the
+ * row is also appended at index (*counter % capacity) of loss_ring [capacity][3] and finite_ring
+ * [capacity] (bit 0 / 1 / 2 = style / content / total non-finite), and *counter is incremented: the
+ * host reads rows at its logging cadence, never per step. */
+int stv_step_scores(const float* losses, int n_style, int n_content, float style_w, float content_w,
+                    float* scores3, float* loss_ring, int* finite_ring, int capacity, int* counter,
+                    void* stream);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 /* Explicit tile selection for the tensor-core conv: out = alpha*conv(x,w)+bias, optional relu gate /
- * accumulate, as in stv_conv3x3_fwd / _dgrad.  taps = 9 or 1; block_n in {64,128,256} or 0 = auto;
- * th*tw == 128 or 0 = auto. */
-int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
-                      const float* bias, const float* alpha, const float* mask_src,
-                      const float* add_src, float* out_pre, float* out_post, int block_n, int th,
-                      int tw, void* stream);
-/* Same for the persistent tap-reusing kernel: block_n in {64,128,256}, m_halves in {1,2} (128 or 256
- * pixels per CTA), tw in {8,16,32}; 0 = auto. */
+ * accumulate, as in stv_conv3x3_fwd / _dgrad.  taps = 9 or 1; block_n in {64,128,256}, m_halves in
+ * {1,2} (128 or 256 pixels per CTA), tw in {8,16,32}; 0 = auto. */
 int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
                        const float* bias, const float* alpha, const float* mask_src,
                        const float* add_src, float* out_pre, float* out_post, int block_n,
                        int m_halves, int tw, void* stream);
-/* Tuning knobs of the tensor-core conv (process-wide; tests and sweeps).  pair_mode: 1 = run every
+/* Tuning knobs of the tensor-core conv (per calling host thread; tests and sweeps).  pair_mode: 1 = run every
  * layer on CTA pairs (clusters of two CTAs, tcgen05 cta_group::2: M = 256 per instruction, each CTA
  * stages half of every weight tile), 0 = single-CTA tiles only, -1 = the built-in per-shape rule
  * table (default).  a_stages / b_stages (operand ring depths) and taps_per_stage (1 or 3 weight taps

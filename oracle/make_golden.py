@@ -54,6 +54,13 @@ CASES: dict[str, dict] = {
     # BASELINE.json configs[0]: 256x256, Adam, 50 steps, content init, on CPU
     "adam_content_256_c1": dict(h=256, w=256, opt="adam", lr=0.01, steps=50, init="content",
                                 save_every=25, csv=True),
+    # BASELINE.json configs[2] at full size: 1920x1080 (pools floor 135 -> 67, the 5e5 Gram clamp
+    # is live on conv1_1), first 2 of its 500 steps with a frame every step (~3 s per CPU step)
+    "adam_content_1080p_c3": dict(h=1080, w=1920, opt="adam", lr=0.01, steps=2, init="content",
+                                  save_every=1),
+    # BASELINE.json configs[4] size: 3840x2160, first closure + one Adam step; random init so that
+    # the content loss and its gradient are non-zero (the sharded path is checked against this)
+    "adam_random_4k_c5": dict(h=2160, w=3840, opt="adam", lr=0.01, steps=1, init="random"),
 }
 
 
@@ -154,14 +161,16 @@ def run_reference(name: str, cfg: dict) -> dict:
     }
     if sink is not None:
         out["frames"] = np.stack(sink.frames) if sink.frames else np.zeros((0,), dtype=np.uint8)
-    if cfg["h"] * cfg["w"] > 128 * 128:  # keep big cases small: strided samples + checksums
+    px = cfg["h"] * cfg["w"]
+    k = 8 if px > 1024 * 1024 else (4 if px > 128 * 128 else 1)  # tests/_cases.py::sample_stride
+    if k > 1:  # keep big cases small: strided samples + checksums of the full tensors
         for key in ("first_grad", "final"):
             full = out[key]
             out[key + "_sum"] = np.array(float(full.astype(np.float64).sum()))
             out[key + "_l2"] = np.array(float(np.sqrt((full.astype(np.float64) ** 2).sum())))
-            out[key] = np.ascontiguousarray(full[..., ::4, ::4])
+            out[key] = np.ascontiguousarray(full[..., ::k, ::k])
         if "frames" in out and out["frames"].size:
-            out["frames"] = np.ascontiguousarray(out["frames"][:, ::4, ::4, :])
+            out["frames"] = np.ascontiguousarray(out["frames"][:, ::k, ::k, :])
     return out
 
 

@@ -27,7 +27,12 @@ _SIGNATURES: dict[str, list] = {
     "stv_device_check": [],
     "stv_pack_conv_weights": [_vp, _vp, _vp, _i, _i, _vp],
     "stv_conv3x3_first_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
+    "stv_conv3x3_first_fwd_bits": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+    "stv_conv3x3_fwd_bits": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "stv_conv3x3_fwd_pool_code": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "stv_conv3x3_dgrad_bits": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "stv_conv3x3_dgrad_unpool": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp],
     "stv_conv3x3_fwd_pool": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_dgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "stv_conv3x3_first_dgrad": [_vp, _vp, _i, _i, _i, _vp, _vp],
@@ -58,8 +63,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_nchw_to_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "stv_nhwc_to_nchw": [_vp, _i, _i, _i, _vp, _vp],
     "stv_finite_flags": [_vp, _i, _vp, _vp],
-    "stv_conv_igemm_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
-                          _vp],
+    "stv_step_scores": [_vp, _i, _i, _f, _f, _vp, _vp, _vp, _i, _vp, _vp],
     "stv_conv_igemm2_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                            _vp],
     "stv_conv_set_tuning": [_i, _i, _i, _i],

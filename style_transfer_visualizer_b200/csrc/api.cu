@@ -21,9 +21,9 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 int device_sm_count() {
-  static int cached[64] = {0};
+  static int cached[kMaxDevices] = {0};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
   if (cached[dev] == 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
@@ -97,17 +97,6 @@ static int check_device_impl() {
 using namespace stv;
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
 
-// STV_CONV_V1=1 routes the hot-path convolutions through the first-generation kernel
-// (conv_igemm.cu) for A/B measurements; the default is the persistent tap-reusing kernel.
-static bool use_conv_v1() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("STV_CONV_V1");
-    cached = (e && e[0] == '1') ? 1 : 0;
-  }
-  return cached == 1;
-}
-
 extern "C" {
 
 const char* stv_last_error(void) { return last_error(); }
@@ -119,21 +108,50 @@ int stv_pack_conv_weights(const float* w, float* w_fwd, float* w_dgrad, int Cout
   return pack_conv_weights_launch(w, w_fwd, w_dgrad, Cout, Cin, S(stream));
 }
 
+// fused convolution entry points: thin argument marshalling over conv_igemm2_launch --------------
+static ConvArgs fwd_args(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                         int Cin, int Cout, float* out_pre, float* out_post, int round_pre) {
+  ConvArgs a;
+  a.x = x; a.w_packed = w_fwd; a.H = H; a.W = W; a.C = Cin; a.N = Cout; a.taps = 9;
+  a.bias = bias; a.out_pre = out_pre; a.out_post = out_post;
+  // out_post feeds the next conv's MMA -> stored tf32-rounded; out_pre (read by the losses) exact
+  // unless it only feeds the Gram contraction (round_pre)
+  a.round_flags = 2 | (round_pre ? 1 : 0);
+  return a;
+}
+static ConvArgs dgrad_args(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                           int accumulate, float* dx) {
+  ConvArgs a;
+  a.x = dy; a.w_packed = w_dgrad; a.H = H; a.W = W; a.C = Cout; a.N = Cin; a.taps = 9;
+  a.add_src = accumulate ? dx : nullptr;
+  a.out_pre = dx;
+  a.round_flags = 1;  // gradient buffers are the next dgrad's MMA operand
+  return a;
+}
+
 int stv_conv3x3_first_fwd(const float* img_nchw, const float* w, const float* bias, int H, int W,
                           int Cout, float* out_pre, float* out_post, int round_pre, void* stream) {
-  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, round_pre,
+  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, nullptr, round_pre,
                                S(stream));
+}
+int stv_conv3x3_first_fwd_bits(const float* img_nchw, const float* w, const float* bias, int H,
+                               int W, int Cout, float* out_pre, float* out_post,
+                               unsigned* out_bits, int round_pre, void* stream) {
+  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, out_bits,
+                               round_pre, S(stream));
 }
 
 int stv_conv3x3_fwd(const float* x, const float* w_fwd, const float* bias, int H, int W, int Cin,
                     int Cout, float* out_pre, float* out_post, int round_pre, void* stream) {
-  const int rf = 2 | (round_pre ? 1 : 0);
-  // out_post feeds the next conv's MMA -> stored tf32-rounded; out_pre (read by the losses) exact.
-  if (use_conv_v1())
-    return conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr,
-                             out_pre, out_post, rf, 0, 0, 0, S(stream));
-  return conv_igemm2_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
-                            out_post, rf, nullptr, 0, 0, 0, S(stream));
+  return conv_igemm2_launch(fwd_args(x, w_fwd, bias, H, W, Cin, Cout, out_pre, out_post, round_pre),
+                            S(stream));
+}
+int stv_conv3x3_fwd_bits(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                         int Cin, int Cout, float* out_pre, float* out_post, unsigned* out_bits,
+                         int round_pre, void* stream) {
+  ConvArgs a = fwd_args(x, w_fwd, bias, H, W, Cin, Cout, out_pre, out_post, round_pre);
+  a.out_bits = out_bits;
+  return conv_igemm2_launch(a, S(stream));
 }
 
 int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, int H, int W,
@@ -141,24 +159,41 @@ int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, 
                          int round_pre, void* stream) {
   STV_REQUIRE(out_post != nullptr && out_pool != nullptr,
               "stv_conv3x3_fwd_pool: out_post and out_pool are required");
-  const int rf = 2 | (round_pre ? 1 : 0);
-  if (use_conv_v1()) {
-    if (int rc = conv_igemm_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr,
-                                   out_pre, out_post, rf, 0, 0, 0, S(stream)))
-      return rc;
-    return maxpool2_fwd_launch(out_post, H, W, Cout, out_pool, S(stream));
-  }
-  return conv_igemm2_launch(x, w_fwd, H, W, Cin, Cout, 9, bias, nullptr, nullptr, nullptr, out_pre,
-                            out_post, rf, nullptr, 0, 0, 0, S(stream), out_pool);
+  ConvArgs a = fwd_args(x, w_fwd, bias, H, W, Cin, Cout, out_pre, out_post, round_pre);
+  a.out_pool = out_pool;
+  return conv_igemm2_launch(a, S(stream));
+}
+int stv_conv3x3_fwd_pool_code(const float* x, const float* w_fwd, const float* bias, int H, int W,
+                              int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
+                              unsigned* out_code, int round_pre, void* stream) {
+  STV_REQUIRE(out_pool != nullptr && out_code != nullptr,
+              "stv_conv3x3_fwd_pool_code: out_pool and out_code are required");
+  ConvArgs a = fwd_args(x, w_fwd, bias, H, W, Cin, Cout, out_pre, out_post, round_pre);
+  a.out_pool = out_pool;
+  a.out_code = out_code;
+  return conv_igemm2_launch(a, S(stream));
 }
 
 int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                       const float* relu_src, int accumulate, float* dx, void* stream) {
-  if (use_conv_v1())
-    return conv_igemm_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
-                             accumulate ? dx : nullptr, dx, nullptr, 1, 0, 0, 0, S(stream));
-  return conv_igemm2_launch(dy, w_dgrad, H, W, Cout, Cin, 9, nullptr, nullptr, relu_src,
-                            accumulate ? dx : nullptr, dx, nullptr, 1, nullptr, 0, 0, 0, S(stream));
+  ConvArgs a = dgrad_args(dy, w_dgrad, H, W, Cout, Cin, accumulate, dx);
+  a.mask_src = relu_src;
+  return conv_igemm2_launch(a, S(stream));
+}
+int stv_conv3x3_dgrad_bits(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                           const unsigned* relu_bits, int accumulate, float* dx, void* stream) {
+  ConvArgs a = dgrad_args(dy, w_dgrad, H, W, Cout, Cin, accumulate, dx);
+  a.mask_bits = relu_bits;
+  return conv_igemm2_launch(a, S(stream));
+}
+int stv_conv3x3_dgrad_unpool(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
+                             const unsigned* pool_code, int H2, int W2, float* dx, void* stream) {
+  STV_REQUIRE(pool_code != nullptr, "stv_conv3x3_dgrad_unpool: pool_code is required");
+  ConvArgs a = dgrad_args(dy, w_dgrad, H, W, Cout, Cin, 0, dx);
+  a.unpool_code = pool_code;
+  a.H2 = H2;
+  a.W2 = W2;
+  return conv_igemm2_launch(a, S(stream));
 }
 
 int stv_conv3x3_first_dgrad(const float* dy, const float* w, int H, int W, int Cout,
@@ -167,16 +202,10 @@ int stv_conv3x3_first_dgrad(const float* dy, const float* w, int H, int W, int C
 }
 int stv_conv3x3_first_dgrad_tc(const float* dy, const float* w16_dgrad, int H, int W, int Cout,
                                float* dimg_nchw, void* stream) {
-  // STV_FD_MH / STV_FD_TW: tile overrides for experiments
-  static int mh = -1, tw = -1;
-  if (mh < 0) {
-    const char* a = getenv("STV_FD_MH");
-    const char* b = getenv("STV_FD_TW");
-    mh = a ? atoi(a) : 0;
-    tw = b ? atoi(b) : 0;
-  }
-  return conv_igemm2_launch(dy, w16_dgrad, H, W, Cout, 16, 9, nullptr, nullptr, nullptr, nullptr,
-                            nullptr, nullptr, 0, dimg_nchw, 0, mh, tw, S(stream));
+  ConvArgs a;
+  a.x = dy; a.w_packed = w16_dgrad; a.H = H; a.W = W; a.C = Cout; a.N = 16; a.taps = 9;
+  a.out_nchw3 = dimg_nchw;
+  return conv_igemm2_launch(a, S(stream));
 }
 
 int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream) {
@@ -218,18 +247,18 @@ int stv_style_bwd(const float* x, const float* s, long hw, int C, const float* g
   // dY[p, :] = grad_w * X[p, :] * S  -- a 1x1 "conv" over a (1 x hw) image with weight matrix S
   // (symmetric, so its rows serve directly as the K-major B operand).
   STV_REQUIRE(hw <= 0x7fffffffL, "style_bwd: feature map too large");
-  if (!use_conv_v1()) {
-    // 1x1: view the feature map as a (hw/32 x 32) image when possible so that 2-D patches apply
-    int h2 = 1, w2 = static_cast<int>(hw);
-    if (hw % 32 == 0) { h2 = static_cast<int>(hw / 32); w2 = 32; }
-    else if (hw % 16 == 0) { h2 = static_cast<int>(hw / 16); w2 = 16; }
-    else if (hw % 8 == 0) { h2 = static_cast<int>(hw / 8); w2 = 8; }
-    return conv_igemm2_launch(x, s, h2, w2, C, C, 1, nullptr, grad_w, nullptr,
-                              accumulate ? dy : nullptr, dy, nullptr, 1, nullptr, 0, 0, 0,
-                              S(stream));
-  }
-  return conv_igemm_launch(x, s, 1, static_cast<int>(hw), C, C, 1, nullptr, grad_w, nullptr,
-                           accumulate ? dy : nullptr, dy, nullptr, 1, 0, 1, 128, S(stream));
+  // 1x1: view the feature map as a (hw/32 x 32) image when possible so that 2-D patches apply
+  int h2 = 1, w2 = static_cast<int>(hw);
+  if (hw % 32 == 0) { h2 = static_cast<int>(hw / 32); w2 = 32; }
+  else if (hw % 16 == 0) { h2 = static_cast<int>(hw / 16); w2 = 16; }
+  else if (hw % 8 == 0) { h2 = static_cast<int>(hw / 8); w2 = 8; }
+  ConvArgs a;
+  a.x = x; a.w_packed = s; a.H = h2; a.W = w2; a.C = C; a.N = C; a.taps = 1;
+  a.alpha = grad_w;
+  a.add_src = accumulate ? dy : nullptr;
+  a.out_pre = dy;
+  a.round_flags = 1;
+  return conv_igemm2_launch(a, S(stream));
 }
 
 int stv_reduce_scratch_floats(void) { return reduce_scratch_floats(); }
@@ -292,20 +321,23 @@ int stv_nhwc_to_nchw(const float* src, int C, int H, int W, float* dst, void* st
 int stv_finite_flags(const float* vals, int n, int* flags, void* stream) {
   return finite_flags_launch(vals, n, flags, S(stream));
 }
-
-int stv_conv_igemm_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
-                      const float* bias, const float* alpha, const float* mask_src,
-                      const float* add_src, float* out_pre, float* out_post, int block_n, int th,
-                      int tw, void* stream) {
-  return conv_igemm_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
-                           out_post, 0, block_n, th, tw, S(stream));
+int stv_step_scores(const float* losses, int n_style, int n_content, float style_w, float content_w,
+                    float* scores3, float* loss_ring, int* finite_ring, int capacity, int* counter,
+                    void* stream) {
+  return step_scores_launch(losses, n_style, n_content, style_w, content_w, scores3, loss_ring,
+                            finite_ring, capacity, counter, S(stream));
 }
+
 int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
                        const float* bias, const float* alpha, const float* mask_src,
                        const float* add_src, float* out_pre, float* out_post, int block_n,
                        int m_halves, int tw, void* stream) {
-  return conv_igemm2_launch(x, w_packed, H, W, C, N, taps, bias, alpha, mask_src, add_src, out_pre,
-                            out_post, 0, nullptr, block_n, m_halves, tw, S(stream));
+  ConvArgs a;
+  a.x = x; a.w_packed = w_packed; a.H = H; a.W = W; a.C = C; a.N = N; a.taps = taps;
+  a.bias = bias; a.alpha = alpha; a.mask_src = mask_src; a.add_src = add_src;
+  a.out_pre = out_pre; a.out_post = out_post;
+  a.force_n = block_n; a.force_mh = m_halves; a.force_tw = tw;
+  return conv_igemm2_launch(a, S(stream));
 }
 int stv_conv_set_tuning(int pair_mode, int a_stages, int b_stages, int taps_per_stage) {
   STV_REQUIRE(pair_mode >= -1 && pair_mode <= 1, "stv_conv_set_tuning: pair_mode must be -1, 0 or 1");

@@ -22,7 +22,8 @@ constexpr int kFirstCout = 64;
 __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                       const float* __restrict__ bias, int H, int W, int groups_per_row,
-                      int round_pre, float* __restrict__ out_pre, float* __restrict__ out_post) {
+                      int round_pre, float* __restrict__ out_pre, float* __restrict__ out_post,
+                      uint2* __restrict__ out_bits) {
   // let a following tensor-core conv (launched with programmatic stream serialization) run its
   // prologue under this kernel's tail; it still waits for our completion before touching data
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -38,8 +39,10 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
 
   const long hw = static_cast<long>(H) * W;
   const int cq = threadIdx.x & 3;
-  const long grp = static_cast<long>(blockIdx.x) * 32 + (threadIdx.x >> 2);
-  if (grp >= static_cast<long>(groups_per_row) * H) return;
+  const long grp_raw = static_cast<long>(blockIdx.x) * 32 + (threadIdx.x >> 2);
+  // groups past the end stay alive (the sign-bit shuffles below are warp-wide) but store nothing
+  const bool active = grp_raw < static_cast<long>(groups_per_row) * H;
+  const long grp = active ? grp_raw : 0;
   const int y = static_cast<int>(grp / groups_per_row);
   const int x0 = static_cast<int>(grp % groups_per_row) * 4;
 
@@ -59,6 +62,9 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
     }
 
   const long pix0 = static_cast<long>(y) * W + x0;
+  // sign bits of the post-ReLU values (the ReLU gate of conv1_2's dgrad): word 0 = channels 0..31,
+  // word 1 = channels 32..63 of each of this thread's four pixels
+  uint32_t sb0[4] = {0u, 0u, 0u, 0u}, sb1[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
   for (int i = 0; i < kFirstCout / 16; ++i) {
     const int c4 = i * 4 + cq;
@@ -83,7 +89,7 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
         }
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
-      if (x0 + px < W) {
+      if (active && x0 + px < W) {
         const long o = (pix0 + px) * (kFirstCout / 4) + c4;
         if (out_pre) {
           float4 r = acc[px];
@@ -92,14 +98,30 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
           }
           reinterpret_cast<float4*>(out_pre)[o] = r;
         }
-        if (out_post) {
+        if (out_post || out_bits) {
           float4 r;
           // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
           r.x = round_tf32(fmaxf(acc[px].x, 0.f)); r.y = round_tf32(fmaxf(acc[px].y, 0.f));
           r.z = round_tf32(fmaxf(acc[px].z, 0.f)); r.w = round_tf32(fmaxf(acc[px].w, 0.f));
-          reinterpret_cast<float4*>(out_post)[o] = r;
+          if (out_post) reinterpret_cast<float4*>(out_post)[o] = r;
+          const uint32_t nib = (r.x > 0.f ? 1u : 0u) | (r.y > 0.f ? 2u : 0u) |
+                               (r.z > 0.f ? 4u : 0u) | (r.w > 0.f ? 8u : 0u);
+          const uint32_t sh = nib << (16 * (i & 1) + 4 * cq);  // channels 16 i + 4 cq .. + 3
+          if (i < 2) sb0[px] |= sh;
+          else sb1[px] |= sh;
         }
       }
+    }
+  }
+  if (out_bits) {  // warp-uniform
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      // OR over the four channel-quad lanes of the pixel group (adjacent lanes: cq = lane % 4)
+      sb0[px] |= __shfl_xor_sync(0xffffffffu, sb0[px], 1);
+      sb0[px] |= __shfl_xor_sync(0xffffffffu, sb0[px], 2);
+      sb1[px] |= __shfl_xor_sync(0xffffffffu, sb1[px], 1);
+      sb1[px] |= __shfl_xor_sync(0xffffffffu, sb1[px], 2);
+      if (cq == px && active && x0 + px < W) out_bits[pix0 + px] = make_uint2(sb0[px], sb1[px]);
     }
   }
 }
@@ -178,15 +200,17 @@ __global__ void conv_ref_kernel(const float* __restrict__ x, const float* __rest
 }
 
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
-                          int Cout, float* out_pre, float* out_post, int round_pre,
-                          cudaStream_t stream) {
+                          int Cout, float* out_pre, float* out_post, unsigned* out_bits,
+                          int round_pre, cudaStream_t stream) {
   STV_REQUIRE(Cout == kFirstCout, "conv_first_fwd: Cout must be %d (got %d)", kFirstCout, Cout);
   STV_REQUIRE(out_pre || out_post, "conv_first_fwd: no output buffer");
+  STV_REQUIRE((reinterpret_cast<uintptr_t>(out_bits) & 7) == 0, "conv_first_fwd: out_bits alignment");
   const int groups_per_row = (W + 3) / 4;
   const long groups = static_cast<long>(groups_per_row) * H;
   const unsigned blocks = static_cast<unsigned>((groups + 31) / 32);
   conv_first_fwd_kernel<<<blocks, 128, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
-                                                    round_pre, out_pre, out_post);
+                                                    round_pre, out_pre, out_post,
+                                                    reinterpret_cast<uint2*>(out_bits));
   STV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

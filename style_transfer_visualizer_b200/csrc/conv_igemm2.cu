@@ -60,9 +60,27 @@ struct Conv2Params {
   float* out_pool;     // optional fused 2x2 / stride-2 max pool of the post-ReLU output
                        // ([H/2][W/2][N], floor mode); plain forward epilogue, tw in {8, 16} only
   float* out_nchw3;    // N == 16 variant: [3][H][W] planes
-  int debug;           // STV_CONV_DEBUG bits (bottleneck experiments; results are then garbage):
-                       // 1 skip weight loads, 2 skip activation loads, 4 skip stores, 8 skip MMAs
+  // ReLU / pool bookkeeping for the backward pass, so that it never re-reads an fp32 activation
+  // just to test a sign or find an argmax:
+  uint32_t* out_bits;          // forward: [H][W][N/32] words, bit c%32 = (out_post[.., c] > 0)
+  uint32_t* out_code;          // forward + fused pool: [H/2][W/2][N/8] words, one nibble per channel:
+                               // bits 0-1 = first-maximum position in the 2x2 window (ATen scan
+                               // order), bit 2 = pooled value > 0 (the ReLU gate)
+  const uint32_t* mask_bits;   // dgrad: ReLU gate from out_bits of the gated layer (instead of mask_src)
+  const uint32_t* unpool_code; // dgrad: the output is the gradient of a POOLED map; route it through
+                               // the 2x2 max-pool (+ ReLU gate) straight into out_pre [H2][W2][N]
+  int H2, W2;
+#ifdef STV_EXPERIMENTS
+  int debug;           // bottleneck experiments (results are then garbage): 1 skip weight loads,
+                       // 2 skip activation loads, 4 skip stores, 8 skip MMAs
+#endif
 };
+
+#ifdef STV_EXPERIMENTS
+#define STV_DBG(p, bit) ((p).debug & (bit))
+#else
+#define STV_DBG(p, bit) 0
+#endif
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  A warp may only read the TMEM lanes
 // 32*(warp%4)..+31, so epilogue warps come in groups of four; 128- and 256-wide tiles use two
@@ -192,8 +210,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
           for (int dxi = 0; dxi < ndx; ++dxi) {
             mbar_wait(a_empty + 8 * as, aph ^ 1);
             const int cur = as;
-            const uint32_t a_bytes = (p.debug & 2) ? 0u : static_cast<uint32_t>(p.a_stage_bytes);
-            const uint32_t b_bytes = (p.debug & 1) ? 0u : static_cast<uint32_t>(TPS * Cfg::kBBytes);
+            const uint32_t a_bytes = STV_DBG(p, 2) ? 0u : static_cast<uint32_t>(p.a_stage_bytes);
+            const uint32_t b_bytes = STV_DBG(p, 1) ? 0u : static_cast<uint32_t>(TPS * Cfg::kBBytes);
             const uint32_t tx_a = a_bytes + (p.uni ? b_bytes : 0u);
             if (tx_a == 0) {
               if constexpr (PAIR) mbar_arrive_cluster(a_full_c + 8 * cur);
@@ -288,7 +306,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   const uint32_t bv = b_lo + u * (Cfg::kBBytes >> 4);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    if (p.debug & 8) continue;
+                    if (STV_DBG(p, 8)) continue;
                     const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (av + 2 * k);
                     const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (bv + 2 * k);
                     if constexpr (PAIR)
@@ -338,7 +356,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int m = hf * 128 + q * 32 + lane;
         const int py = ty0 + (m >> p.tw_shift);
         const int px = tx0 + (m & (p.tw - 1));
-        const bool valid = (py < p.H) && (px < p.W) && !(p.debug & 4);
+        const bool valid = (py < p.H) && (px < p.W) && !STV_DBG(p, 4);
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               acc * (MH * BLOCK_N) + hf * BLOCK_N;
         if constexpr (BLOCK_N == 16) {
@@ -360,19 +378,68 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             p.out_nchw3[2 * hw + o] = __uint_as_float(r[2]);
           }
         } else {
+          if (p.unpool_code != nullptr) {
+            // dgrad whose output pixel is a POOLED pixel: the 2x2 max-pool backward (+ the ReLU gate
+            // in front of the pool) is applied here, so the pooled gradient never goes to memory
+            // and no pool-backward kernel re-reads the fp32 activation for its argmax.  Each lane
+            // owns one pooled pixel and writes the four pixels of its window (zeros except at the
+            // recorded first-maximum position), 128 contiguous bytes per pixel and chunk.
+            const size_t pix = static_cast<size_t>(py) * p.W + px;
+            const size_t o00 = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * p.N + n0;
+            const size_t wrow = static_cast<size_t>(p.W2) * p.N;
+#pragma unroll 1
+            for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
+              uint32_t r[32];
+              tmem_ld_32x32(trow + cb, r);
+              tmem_ld_wait();
+              if (!valid) continue;
+              const uint4 cw4 =
+                  __ldg(reinterpret_cast<const uint4*>(p.unpool_code + ((pix * p.N + n0 + cb) >> 3)));
+              const uint32_t cw[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[e] = __uint_as_float(r[4 * j + e]) * alpha;
+                  if (p.round_pre) v[e] = round_tf32(v[e]);
+                }
+                const uint32_t c16 = (cw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float4 o;
+                  o.x = ((c16 & 7u) == (4u | q)) ? v[0] : 0.f;
+                  o.y = (((c16 >> 4) & 7u) == (4u | q)) ? v[1] : 0.f;
+                  o.z = (((c16 >> 8) & 7u) == (4u | q)) ? v[2] : 0.f;
+                  o.w = (((c16 >> 12) & 7u) == (4u | q)) ? v[3] : 0.f;
+                  const size_t off = o00 + (q >> 1) * wrow + (q & 1) * p.N + cb + 4 * j;
+                  *reinterpret_cast<float4*>(p.out_pre + off) = o;
+                }
+              }
+            }
+            continue;
+          }
           if (p.mask_src == nullptr && p.add_src == nullptr) {
-            // Plain forward epilogue: each lane owns one pixel row and writes its 32-channel chunk
-            // as eight 16-byte stores (the whole 128-byte line is produced back to back by one
-            // thread, which L2 merges); cheaper than the transpose when nothing has to be read.
-            const size_t row_off = (static_cast<size_t>(py) * p.W + px) * p.N + n0;
+            // Plain epilogue (forward; dgrad without accumulation): each lane owns one pixel row and
+            // writes its 32-channel chunk as eight 16-byte stores (the whole 128-byte line is
+            // produced back to back by one thread, which L2 merges); cheaper than the transpose
+            // when nothing but a sign word has to be read.
+            const size_t pix = static_cast<size_t>(py) * p.W + px;
+            const size_t row_off = pix * p.N + n0;
             // Fused max pool: the 2x2 window of a pooled pixel lives in four lanes of this warp
             // (x neighbour = lane ^ 1, y neighbour = lane ^ tw; tile origins are even), so two
             // shuffles per value replace the separate pool kernel's re-read of `post`.  Max commutes
             // with the monotonic tf32 rounding, so the result equals pooling the stored tensor.
             const bool pool = p.out_pool != nullptr;
+            const bool want_code = pool && p.out_code != nullptr;
+            // the post-ReLU value is needed for the pool and the sign bits even when it is not stored
+            // (a pooled layer's full-resolution activation has no reader once the backward pass
+            // works from the pool codes)
+            const bool want_post = p.out_post != nullptr || pool || p.out_bits != nullptr;
+            const bool odd_x = (px & 1) != 0;
             const int Ho = p.H >> 1, Wo = p.W >> 1;
             const bool pool_writer = pool && !(py & 1) && !(px & 1) && (py >> 1) < Ho &&
-                                     (px >> 1) < Wo && !(p.debug & 4);
+                                     (px >> 1) < Wo && !STV_DBG(p, 4);
             const size_t pool_off =
                 (static_cast<size_t>(py >> 1) * Wo + (px >> 1)) * p.N + n0;
 #pragma unroll 1
@@ -380,6 +447,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               uint32_t r[32];
               tmem_ld_32x32(trow + cb, r);
               tmem_ld_wait();
+              uint32_t gate = 0xFFFFFFFFu;  // dgrad: ReLU gate of this pixel's 32 channels
+              if (p.mask_bits != nullptr && valid)
+                gate = __ldg(p.mask_bits + pix * (p.N >> 5) + ((n0 + cb) >> 5));
+              uint32_t bits = 0;            // forward: sign bits of the post-ReLU values
+              uint32_t codew[4] = {0u, 0u, 0u, 0u};
               if (valid || pool) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -389,6 +461,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   v.y = fmaf(__uint_as_float(r[4 * j + 1]), alpha, b.y);
                   v.z = fmaf(__uint_as_float(r[4 * j + 2]), alpha, b.z);
                   v.w = fmaf(__uint_as_float(r[4 * j + 3]), alpha, b.w);
+                  const uint32_t g4 = gate >> (4 * j);
+                  v.x = (g4 & 1u) ? v.x : 0.f;
+                  v.y = (g4 & 2u) ? v.y : 0.f;
+                  v.z = (g4 & 4u) ? v.z : 0.f;
+                  v.w = (g4 & 8u) ? v.w : 0.f;
                   const int col = cb + 4 * j;
                   if (p.out_pre && valid) {
                     float4 o = v;
@@ -398,7 +475,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                     }
                     *reinterpret_cast<float4*>(p.out_pre + row_off + col) = o;
                   }
-                  if (p.out_post) {
+                  if (want_post) {
                     float4 o;
                     o.x = fmaxf(v.x, 0.f); o.y = fmaxf(v.y, 0.f);
                     o.z = fmaxf(v.z, 0.f); o.w = fmaxf(v.w, 0.f);
@@ -406,23 +483,50 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                       o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                       o.z = round_tf32(o.z); o.w = round_tf32(o.w);
                     }
-                    if (valid) *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                    if (p.out_post != nullptr && valid)
+                      *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
+                    bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) |
+                             (o.w > 0.f ? 8u : 0u)) << (4 * j);
                     if (pool) {  // warp-uniform branch: every lane takes part in the shuffles
-                      float4 m = o;
-                      m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 1));
-                      m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, 1));
-                      m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, 1));
-                      m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 1));
-                      m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, p.tw));
-                      m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, p.tw));
-                      m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, p.tw));
-                      m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, p.tw));
+                      // x stage: (a, b) = (even-x pixel, odd-x pixel) of this row; strict > keeps the
+                      // first maximum, the scan order of ATen's max_pool2d (a, b, then the next row)
+                      const float ov[4] = {o.x, o.y, o.z, o.w};
+                      float m0[4];
+                      uint32_t kb = 0;
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float nb = __shfl_xor_sync(0xffffffffu, ov[e], 1);
+                        const float a = odd_x ? nb : ov[e];
+                        const float bb = odd_x ? ov[e] : nb;
+                        const bool k0 = bb > a;
+                        m0[e] = k0 ? bb : a;
+                        kb |= (k0 ? 1u : 0u) << e;
+                      }
+                      // y stage: this lane acts as the top row (only the (even, even) lane stores)
+                      const uint32_t kbo = __shfl_xor_sync(0xffffffffu, kb, p.tw);
+                      float mx[4];
+                      uint32_t c16 = 0;
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float mo = __shfl_xor_sync(0xffffffffu, m0[e], p.tw);
+                        const bool lower = mo > m0[e];
+                        mx[e] = lower ? mo : m0[e];
+                        const uint32_t k = lower ? (2u | ((kbo >> e) & 1u)) : ((kb >> e) & 1u);
+                        c16 |= (k | (mx[e] > 0.f ? 4u : 0u)) << (4 * e);
+                      }
                       if (pool_writer)
-                        *reinterpret_cast<float4*>(p.out_pool + pool_off + col) = m;
+                        *reinterpret_cast<float4*>(p.out_pool + pool_off + col) =
+                            make_float4(mx[0], mx[1], mx[2], mx[3]);
+                      if (want_code) codew[j >> 1] |= c16 << (16 * (j & 1));
                     }
                   }
                 }
               }
+              if (p.out_bits != nullptr && valid)
+                p.out_bits[pix * (p.N >> 5) + ((n0 + cb) >> 5)] = bits;
+              if (want_code && pool_writer)
+                *reinterpret_cast<uint4*>(p.out_code + ((pool_off + cb) >> 3)) =
+                    make_uint4(codew[0], codew[1], codew[2], codew[3]);
             }
             continue;
           }
@@ -452,12 +556,17 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               uint32_t offs[4];
               bool ok[4];
               float4 mk[4], ad[4];
+              uint32_t gb[4];  // ReLU gate bits of this thread's four channels
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const int mm = hf * 128 + q * 32 + (h4 + it) * 4 + sub;
                 const int yy = ty0 + (mm >> p.tw_shift), xx = tx0 + (mm & (p.tw - 1));
                 ok[it] = (yy < p.H) && (xx < p.W);
-                offs[it] = (static_cast<uint32_t>(yy) * p.W + xx) * p.N + n0 + col;
+                const uint32_t pixi = static_cast<uint32_t>(yy) * p.W + xx;
+                offs[it] = pixi * p.N + n0 + col;
+                gb[it] = 0xFu;
+                if (p.mask_bits != nullptr && ok[it])  // one word per pixel and 32-channel chunk:
+                  gb[it] = __ldg(p.mask_bits + pixi * (p.N >> 5) + ((n0 + cb) >> 5)) >> (4 * chunk);
               }
               if (p.mask_src) {
 #pragma unroll
@@ -491,6 +600,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   v.z = mk[it].z > 0.f ? v.z : 0.f;
                   v.w = mk[it].w > 0.f ? v.w : 0.f;
                 }
+                v.x = (gb[it] & 1u) ? v.x : 0.f;
+                v.y = (gb[it] & 2u) ? v.y : 0.f;
+                v.z = (gb[it] & 4u) ? v.z : 0.f;
+                v.w = (gb[it] & 8u) ? v.w : 0.f;
                 if (p.add_src) {
                   v.x += ad[it].x; v.y += ad[it].y; v.z += ad[it].z; v.w += ad[it].w;
                 }
@@ -542,6 +655,26 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// Tile-policy overrides for sweeps and tests (stv_conv_set_tuning).  Thread-local: a launch only
+// ever reads the calling thread's copy, so the C ABI stays re-entrant across host threads.
+struct ConvTuning {
+  int pair_mode = -1;                      // -1: rule table, 0: never, 1: whenever the shape allows
+  int a_stages = 0, b_stages = 0, tps = 0;  // ring depth / taps-per-stage overrides (0 = defaults)
+};
+static thread_local ConvTuning g_tuning;
+void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
+  g_tuning.pair_mode = pair_mode;
+  g_tuning.a_stages = a_stages;
+  g_tuning.b_stages = b_stages;
+  g_tuning.tps = tps;
+}
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 // b_rows: weight rows one CTA stages per tap (the N tile, or half of it for a CTA pair)
 // staging: the transposing epilogue (ReLU gate / accumulate) needs one 4 KB tile per epilogue warp
 static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int b_rows,
@@ -558,16 +691,13 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
                                     Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N,
                                     p.mask_src != nullptr || p.add_src != nullptr);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  const int dev = current_device();
+  // per kernel instantiation AND per device: the opt-in is a property of the (function, context)
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[dev]) {
     STV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         227 * 1024));
-    attr_smem = 227 * 1024;
-  }
-  static int use_pdl = -1;
-  if (use_pdl < 0) {
-    const char* e = getenv("STV_PDL");
-    use_pdl = (e && e[0] == '0') ? 0 : 1;
+    attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -583,40 +713,30 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (use_pdl) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
+  // programmatic dependent launch: the prologue overlaps the previous kernel's tail
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
   cfg.attrs = attr;
   cfg.numAttrs = na;
   if (PAIR) {
     // clusters of 2 cannot always use every SM (a GPC with an odd SM count strands one): size the
     // persistent grid by what the device can co-schedule
-    static int max_clusters = -1;
-    static int max_clusters_smem = -1;
-    if (max_clusters < 0 || max_clusters_smem != smem) {
+    static int max_clusters[kMaxDevices] = {};
+    static int max_clusters_smem[kMaxDevices] = {};
+    if (max_clusters[dev] <= 0 || max_clusters_smem[dev] != smem) {
       cudaLaunchConfig_t q = cfg;
       q.gridDim = dim3(2 * device_sm_count());
       int n = 0;
       STV_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
       STV_REQUIRE(n > 0, "conv_igemm2: no CTA pair of %d bytes fits the device", smem);
-      max_clusters = n;
-      max_clusters_smem = smem;
+      max_clusters[dev] = n;
+      max_clusters_smem[dev] = smem;
     }
-    if (grid > 2 * max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+    if (grid > 2 * max_clusters[dev]) cfg.gridDim = dim3(2 * max_clusters[dev]);
   }
   STV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, p));
   return 0;
-}
-
-static int g_pair_mode = -1;  // -1: rule table, 0: never, 1: whenever the shape allows
-static int g_as = 0, g_bs = 0, g_tps = 0;  // ring depth / taps-per-stage overrides (0 = defaults)
-void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
-  g_pair_mode = pair_mode;
-  g_as = a_stages;
-  g_bs = b_stages;
-  g_tps = tps;
 }
 
 // Tile selection (measured on B200, profiles/r1_selftest_perf_v2.log): N tile as wide as Cout
@@ -631,16 +751,16 @@ static long count_tiles(int H, int W, int N, int mh, int tw, int bn) {
   return static_cast<long>((H + th - 1) / th) * ((W + tw - 1) / tw) * (N / bn);
 }
 
-static int g_want_pool = 0;  // the launch in progress asks for the fused pool: tw = 32 is excluded
-
-static int pick_tw(int H, int W, int mh) {
+// want_pool: the launch asks for the fused pool, whose 2x2 window must sit inside one epilogue
+// warp: tw = 32 is excluded
+static int pick_tw(int H, int W, int mh, bool want_pool) {
   // least padded pixels (= MMA work); the dy halo only inflates A traffic, so it is a tie-breaker
   const int tw_opts[3] = {16, 32, 8};
   int best = 16;
   double best_cost = -1.0;
   for (int i = 0; i < 3; ++i) {
     const int tw = tw_opts[i], th = 128 * mh / tw;
-    if (g_want_pool && tw == 32) continue;  // a 2x2 window must sit inside one epilogue warp
+    if (want_pool && tw == 32) continue;
     const double area = static_cast<double>((H + th - 1) / th) * th * (((W + tw - 1) / tw) * tw);
     const double cost = area * (1.0 + 0.15 * 2.0 / th);
     if (best_cost < 0 || cost < best_cost) {
@@ -651,21 +771,21 @@ static int pick_tw(int H, int W, int mh) {
   return best;
 }
 
-static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_epilogue,
-                               int force_n, int force_mh, int force_tw) {
+static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want_pool) {
+  const int H = a.H, W = a.W, C = a.C, N = a.N;
   const int sms = device_sm_count();
   int bn, mh;
   if (N == 16) { bn = 16; mh = 1; }
   else if (N % 256 == 0) { bn = 256; mh = (C >= 512 && !heavy_epilogue) ? 2 : 1; }
   else if (N % 128 == 0) { bn = 128; mh = 2; }
   else { bn = 64; mh = heavy_epilogue ? 1 : 2; }  // fwd: 24 MMAs per commit beat two co-resident CTAs
-  if (force_n <= 0 && force_mh <= 0 && N != 16) {
+  if (a.force_n <= 0 && a.force_mh <= 0 && N != 16) {
     // keep the machine busy on small feature maps: narrow the tile until ~every SM has one
     const int order[5][2] = {{256, 2}, {256, 1}, {128, 2}, {128, 1}, {64, 1}};
     int i = 0;
     while (i < 5 && !(order[i][0] == bn && order[i][1] == mh)) ++i;
     while (i < 4) {
-      const int tw = pick_tw(H, W, mh);
+      const int tw = pick_tw(H, W, mh, want_pool);
       if (count_tiles(H, W, N, mh, tw, bn) >= (3L * sms) / 4) break;
       ++i;
       if (N % order[i][0] != 0) continue;
@@ -673,8 +793,8 @@ static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_e
       mh = order[i][1];
     }
   }
-  if (force_n > 0) bn = force_n;
-  if (force_mh > 0) mh = force_mh;
+  if (a.force_n > 0) bn = a.force_n;
+  if (a.force_mh > 0) mh = a.force_mh;
   // CTA pairs (profiles/r1_pair_sweep.log, r1_ring_sweep.log): with half-size weight stages a
   // 256-wide tile affords three taps per stage (12 MMAs per barrier round trip) AND 3-deep rings;
   // a stage is only re-armed a full commit -> producer -> TMA -> consumer chain (~1.7 us) after its
@@ -682,45 +802,43 @@ static TileChoice choose_tiles(int H, int W, int C, int N, int taps, int heavy_e
   // tiles, +5 % on 128-wide two-half tiles; neutral or worse elsewhere, which stays single-CTA.
   int pair = 0;
   if (N != 16) {
-    if (g_pair_mode >= 0) pair = g_pair_mode;
-    else pair = (taps == 9 && (bn == 256 || (bn == 128 && mh == 2))) ? 1 : 0;
-    if (pair && bn == 256 && force_mh <= 0) mh = 1;
+    if (g_tuning.pair_mode >= 0) pair = g_tuning.pair_mode;
+    else pair = (a.taps == 9 && (bn == 256 || (bn == 128 && mh == 2))) ? 1 : 0;
+    if (pair && bn == 256 && a.force_mh <= 0) mh = 1;
   }
-  const int tw2 = force_tw > 0 ? force_tw : pick_tw(H, W, mh);
+  const int tw2 = a.force_tw > 0 ? a.force_tw : pick_tw(H, W, mh, want_pool);
   return TileChoice{mh, tw2, 128 * mh / tw2, bn, pair};
 }
 
-int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
-                       const float* bias, const float* alpha, const float* mask_src,
-                       const float* add_src, float* out_pre, float* out_post, int round_flags,
-                       float* out_nchw3, int force_n, int force_mh, int force_tw,
-                       cudaStream_t stream, float* out_pool) {
+int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
+  const int H = a.H, W = a.W, C = a.C, N = a.N, taps = a.taps;
   STV_REQUIRE(C % 32 == 0 && C >= 32, "conv_igemm2: input channels %d must be a multiple of 32", C);
   STV_REQUIRE(N % 64 == 0 || N == 16, "conv_igemm2: output channels %d must be 16 or a multiple of 64", N);
   STV_REQUIRE(taps == 9 || taps == 1, "conv_igemm2: taps must be 9 or 1 (got %d)", taps);
   STV_REQUIRE(H > 0 && W > 0, "conv_igemm2: empty image");
-  STV_REQUIRE((N == 16) == (out_nchw3 != nullptr), "conv_igemm2: N == 16 <=> NCHW3 output");
-  STV_REQUIRE(out_pre || out_post || out_nchw3, "conv_igemm2: no output buffer");
+  STV_REQUIRE((N == 16) == (a.out_nchw3 != nullptr), "conv_igemm2: N == 16 <=> NCHW3 output");
+  STV_REQUIRE(a.out_pre || a.out_post || a.out_nchw3 || a.out_pool, "conv_igemm2: no output buffer");
   STV_REQUIRE(static_cast<double>(H) * W * N < 4.0e9, "conv_igemm2: tensor exceeds 32-bit indexing");
+  STV_REQUIRE(a.out_pool == nullptr || N != 16, "conv_igemm2: no pool on the N = 16 variant");
+  STV_REQUIRE(a.out_code == nullptr || a.out_pool != nullptr,
+              "conv_igemm2: pool codes are produced by the fused pool only");
+  STV_REQUIRE(a.out_bits == nullptr || N != 16, "conv_igemm2: no sign bits on the N = 16 variant");
+  STV_REQUIRE(!(a.mask_bits && a.mask_src), "conv_igemm2: give the ReLU gate as bits OR as fp32");
+  if (a.unpool_code != nullptr) {
+    STV_REQUIRE(a.out_pre != nullptr && a.out_post == nullptr && !a.mask_src && !a.add_src &&
+                    !a.mask_bits && !a.out_pool && !a.bias && N != 16,
+                "conv_igemm2: the un-pooling epilogue writes out_pre only");
+    STV_REQUIRE(a.H2 / 2 == H && a.W2 / 2 == W,
+                "conv_igemm2: %dx%d is not the 2x2 floor-pooled size of %dx%d", H, W, a.H2, a.W2);
+    STV_REQUIRE(static_cast<double>(a.H2) * a.W2 * N < 4.0e9, "conv_igemm2: un-pooled tensor too large");
+  }
 
-  static int env_heavy = -1;
-  if (env_heavy < 0) {
-    const char* e = getenv("STV_CONV_HEAVY_M1");
-    env_heavy = e ? atoi(e) : 1;
-  }
-  const int heavy = env_heavy && (mask_src != nullptr || add_src != nullptr);
-  static int env_fuse_pool = -1;
-  if (env_fuse_pool < 0) {
-    const char* e = getenv("STV_FUSE_POOL");
-    env_fuse_pool = (e && e[0] == '0') ? 0 : 1;
-  }
-  STV_REQUIRE(out_pool == nullptr || (out_post != nullptr && N != 16),
-              "conv_igemm2: the fused pool needs the post-ReLU output");
-  const bool pool_ok = out_pool != nullptr && env_fuse_pool && mask_src == nullptr &&
-                       add_src == nullptr && force_tw != 32;
-  g_want_pool = pool_ok ? 1 : 0;
-  const TileChoice tc = choose_tiles(H, W, C, N, taps, heavy, force_n, force_mh, force_tw);
-  g_want_pool = 0;
+  // big global reads in the epilogue (fp32 gate or accumulate source) go through the transposing
+  // path; it also selects one-half tiles for the 64-wide layers (two co-resident CTAs)
+  const bool staging = a.mask_src != nullptr || a.add_src != nullptr;
+  const bool heavy = staging || a.mask_bits != nullptr;
+  const bool pool_ok = a.out_pool != nullptr && !staging && a.force_tw != 32;
+  const TileChoice tc = choose_tiles(a, heavy, pool_ok);
   Conv2Params p;
   p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps;
   p.tw = tc.tw; p.th = tc.th;
@@ -731,51 +849,46 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   p.tiles_total = p.tiles_m * (N / tc.block_n);
   const int halo = taps == 9 ? 2 : 0;
   p.a_stage_bytes = (tc.th + halo) * tc.tw * 128;
-  p.bias = bias; p.alpha = alpha; p.mask_src = mask_src; p.add_src = add_src;
-  p.out_pre = out_pre; p.out_post = out_post;
-  p.round_pre = round_flags & 1; p.round_post = (round_flags >> 1) & 1;
-  p.out_nchw3 = out_nchw3;
-  p.out_pool = (pool_ok && tc.tw != 32) ? out_pool : nullptr;
+  p.bias = a.bias; p.alpha = a.alpha; p.mask_src = a.mask_src; p.add_src = a.add_src;
+  p.out_pre = a.out_pre; p.out_post = a.out_post;
+  p.round_pre = a.round_flags & 1; p.round_post = (a.round_flags >> 1) & 1;
+  p.out_nchw3 = a.out_nchw3;
+  p.out_pool = (pool_ok && tc.tw != 32) ? a.out_pool : nullptr;
+  p.out_bits = a.out_bits;
+  p.out_code = p.out_pool ? a.out_code : nullptr;
+  p.mask_bits = a.mask_bits;
+  p.unpool_code = a.unpool_code;
+  p.H2 = a.H2; p.W2 = a.W2;
+  STV_REQUIRE(a.out_code == nullptr || p.out_code != nullptr,
+              "conv_igemm2: pool codes requested but the pool cannot be fused for this shape");
+#ifdef STV_EXPERIMENTS
   {
     const char* e = getenv("STV_CONV_DEBUG");
     p.debug = e ? atoi(e) : 0;
   }
+#endif
 
   CUtensorMap tx, twm;
   {
     const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)H};
     const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)W * C * 4};
     const uint32_t box[3] = {32, (uint32_t)tc.tw, (uint32_t)(tc.th + halo)};
-    if (int rc = encode_tmap_f32(&tx, x, 3, dims, strides, box, kSwizzle128B)) return rc;
+    if (int rc = encode_tmap_f32(&tx, a.x, 3, dims, strides, box, kSwizzle128B)) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)C, (uint64_t)taps * N};
     const uint64_t strides[1] = {(uint64_t)C * 4};
     const uint32_t box[2] = {32, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n)};
-    if (int rc = encode_tmap_f32(&twm, w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
+    if (int rc = encode_tmap_f32(&twm, a.w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
   }
   const int sms = device_sm_count();
-  // ring depths: STV_CONV_STAGES="as,bs" overrides (experiments); defaults keep >= ~2000 MMA cycles
-  // of weight stages in flight (TMA latency under load) within the shared-memory budget
-  static int env0_as = -1, env0_bs = -1, env0_tps = -1;
-  if (env0_as < 0) {
-    env0_as = 0; env0_bs = 0; env0_tps = 0;
-    if (const char* e = getenv("STV_CONV_STAGES"))
-      sscanf(e, "%d,%d,%d", &env0_as, &env0_bs, &env0_tps);
-  }
-  const int env_as = g_as > 0 ? g_as : env0_as;
-  const int env_bs = g_bs > 0 ? g_bs : env0_bs;
-  const int env_tps = g_tps > 0 ? g_tps : env0_tps;
+  // ring depths: defaults keep >= ~2000 MMA cycles of weight stages in flight (TMA latency under
+  // load) within the shared-memory budget; stv_conv_set_tuning overrides them for sweeps
+  const int env_as = g_tuning.a_stages, env_bs = g_tuning.b_stages, env_tps = g_tuning.tps;
   p.tps = (taps == 9 && (tc.block_n <= 128 || tc.pair)) ? 3 : 1;
   if (env_tps > 0 && taps == 9 && (tc.block_n <= 128 || tc.pair)) p.tps = env_tps;
-  static int env_uni = -1;
-  if (env_uni < 0) {
-    const char* e = getenv("STV_CONV_UNI");
-    env_uni = (e && e[0] == '0') ? 0 : 1;
-  }
   const int b_rows = tc.pair ? tc.block_n / 2 : tc.block_n;
-  const int staging = mask_src != nullptr || add_src != nullptr;
-  p.uni = (env_uni && (taps == 1 || p.tps == 3)) ? 1 : 0;
+  p.uni = (taps == 1 || p.tps == 3) ? 1 : 0;
   if (p.uni) {
     // one ring of {A tile, its weight taps}: as deep as shared memory allows, up to 4; 64-wide and
     // 16-wide tiles stay at 2 so that two CTAs share an SM
@@ -787,17 +900,9 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
     p.a_stages = depth;
     p.b_stages = depth;
   } else {
-    if (p.tps == 3) {
-      // measured (profiles/r1_stage_sweep.log): N=64 runs best as two co-resident CTAs with
-      // 2-deep rings; N=128 with a 3-deep weight ring
-      p.a_stages = 2;
-      p.b_stages = tc.block_n == 64 ? 2 : (tc.block_n == 16 ? 4 : 3);
-    } else {
-      p.a_stages = tc.block_n >= 256 ? 2 : 3;
-      p.b_stages = 4;
-    }
-    if (tc.pair && p.tps == 1) p.b_stages = 6;  // half-size weight stages: same bytes in flight
-    if (tc.pair && p.tps == 3 && tc.block_n >= 128) { p.a_stages = 3; p.b_stages = 3; }
+    p.a_stages = tc.block_n >= 256 ? 2 : 3;
+    p.b_stages = 4;
+    if (tc.pair) p.b_stages = 6;  // half-size weight stages: same bytes in flight
     if (env_as > 0) p.a_stages = env_as;
     if (env_bs > 0) p.b_stages = env_bs;
     while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N,
@@ -844,9 +949,11 @@ int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int 
   return 2;
   };
   if (int rc = dispatch()) return rc;
-  // no fused pool for this shape (tw = 32 forced, or fusion disabled): separate pool kernel
-  if (out_pool != nullptr && p.out_pool == nullptr)
-    return maxpool2_fwd_launch(out_post, H, W, N, out_pool, stream);
+  // no fused pool for this shape (tw = 32 forced): separate pool kernel
+  if (a.out_pool != nullptr && p.out_pool == nullptr) {
+    STV_REQUIRE(a.out_post != nullptr, "conv_igemm2: the separate pool kernel needs out_post");
+    return maxpool2_fwd_launch(a.out_post, H, W, N, a.out_pool, stream);
+  }
   return 0;
 }
 

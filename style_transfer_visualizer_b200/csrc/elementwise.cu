@@ -309,6 +309,16 @@ absstat_finish_kernel(const float* __restrict__ partials, int nb, float* out2) {
 // ------------------------------------------------------------------------------------------
 // Adam, same operation order as torch's single-tensor path (optim/adam.py): lerp on m,
 // mul+addcmul on v, denom = sqrt(v)/sqrt(bc2) + eps, x += -step_size * (m / denom).
+__device__ __forceinline__ void adam_elem(float& x, float g, float& m, float& v, float w1, float w2,
+                                          float beta2, float eps, float step_size,
+                                          float bias2_sqrt) {
+  m = fmaf(w1, g - m, m);
+  v = __fmul_rn(v, beta2);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(w2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bias2_sqrt), eps);
+  x = __fadd_rn(x, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+}
+// 16-byte accesses: 4 loads + 3 stores of 16 B per thread and iteration, two iterations in flight
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, long n, float beta1, float beta2, float eps,
@@ -318,18 +328,27 @@ adam_step_kernel(float* __restrict__ x, const float* __restrict__ g, float* __re
     bias2_sqrt = __ldg(dev_scalars + 1);
   }
   const float w1 = 1.f - beta1, w2 = 1.f - beta2;
-  for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < n;
-       i += static_cast<long>(gridDim.x) * 256) {
-    const float gi = g[i];
-    float mi = m[i], vi = v[i];
-    mi = fmaf(w1, gi - mi, mi);
-    vi = __fmul_rn(vi, beta2);
-    vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(w2, gi), gi));
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bias2_sqrt), eps);
-    x[i] = __fadd_rn(x[i], __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
-    m[i] = mi;
-    v[i] = vi;
+  const long n4 = n >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const long stride = static_cast<long>(gridDim.x) * 256;
+#pragma unroll 2
+  for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += stride) {
+    const float4 gi = __ldg(g4 + i);
+    float4 xi = x4[i], mi = m4[i], vi = v4[i];
+    adam_elem(xi.x, gi.x, mi.x, vi.x, w1, w2, beta2, eps, step_size, bias2_sqrt);
+    adam_elem(xi.y, gi.y, mi.y, vi.y, w1, w2, beta2, eps, step_size, bias2_sqrt);
+    adam_elem(xi.z, gi.z, mi.z, vi.z, w1, w2, beta2, eps, step_size, bias2_sqrt);
+    adam_elem(xi.w, gi.w, mi.w, vi.w, w1, w2, beta2, eps, step_size, bias2_sqrt);
+    x4[i] = xi;
+    m4[i] = mi;
+    v4[i] = vi;
   }
+  if (blockIdx.x == 0)
+    for (long i = (n4 << 2) + threadIdx.x; i < n; i += 256)
+      adam_elem(x[i], g[i], m[i], v[i], w1, w2, beta2, eps, step_size, bias2_sqrt);
 }
 
 // state[0] = step count (as float, exact below 2^24); writes {step_size, sqrt(bias_correction2)}.
@@ -457,6 +476,38 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int C, long h
 __global__ void finite_flags_kernel(const float* __restrict__ vals, int n, int* flags) {
   const int i = threadIdx.x;
   if (i < n && !isfinite(vals[i])) atomicOr(flags + i, 1);
+}
+
+// End of one optimisation step, inside the captured graph (reference optimization.py:298-312 weighted
+// total, :375-391 finiteness checks, :402-422 loss recording): one thread reduces the per-layer
+// losses to {style score, content score, total}, appends the row to a device ring indexed by a
+// DEVICE step counter and records the three non-finite flags of that row.  The host reads rows at
+// its logging cadence only; nothing here needs a per-step host value.
+__global__ void step_scores_kernel(const float* __restrict__ losses, int n_style, int n_content,
+                                   float style_w, float content_w, float* __restrict__ scores3,
+                                   float* __restrict__ loss_ring, int* __restrict__ finite_ring,
+                                   int capacity, int* __restrict__ counter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // same left-to-right order as torch.stack(losses).sum() on a handful of elements
+  float st = 0.f, ct = 0.f;
+  for (int i = 0; i < n_style; ++i) st += losses[i];
+  for (int i = 0; i < n_content; ++i) ct += losses[n_style + i];
+  const float total = __fadd_rn(__fmul_rn(style_w, st), __fmul_rn(content_w, ct));
+  scores3[0] = st;
+  scores3[1] = ct;
+  scores3[2] = total;
+  if (counter != nullptr) {
+    const int step = *counter;
+    const int row = step % capacity;
+    if (loss_ring != nullptr) {
+      loss_ring[3 * row + 0] = st;
+      loss_ring[3 * row + 1] = ct;
+      loss_ring[3 * row + 2] = total;
+    }
+    if (finite_ring != nullptr)
+      finite_ring[row] = (isfinite(st) ? 0 : 1) | (isfinite(ct) ? 0 : 2) | (isfinite(total) ? 0 : 4);
+    *counter = step + 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -615,6 +666,16 @@ int nhwc_to_nchw_launch(const float* src, int C, int H, int W, float* dst, cudaS
 int finite_flags_launch(const float* vals, int n, int* flags, cudaStream_t stream) {
   STV_REQUIRE(n <= 32, "finite_flags: at most 32 values");
   finite_flags_kernel<<<1, 32, 0, stream>>>(vals, n, flags);
+  STV_LAUNCH_CHECK();
+  return 0;
+}
+int step_scores_launch(const float* losses, int n_style, int n_content, float style_w,
+                       float content_w, float* scores3, float* loss_ring, int* finite_ring,
+                       int capacity, int* counter, cudaStream_t stream) {
+  STV_REQUIRE(losses && scores3 && n_style >= 0 && n_content >= 0, "step_scores: bad arguments");
+  STV_REQUIRE(counter == nullptr || capacity > 0, "step_scores: ring capacity must be positive");
+  step_scores_kernel<<<1, 32, 0, stream>>>(losses, n_style, n_content, style_w, content_w, scores3,
+                                           loss_ring, finite_ring, capacity, counter);
   STV_LAUNCH_CHECK();
   return 0;
 }

@@ -4,24 +4,37 @@
 
 namespace stv {
 
-// conv_igemm.cu ---------------------------------------------------------------------------
-// out = [relu-mask](alpha * conv(x, w) + bias) + add ; writes out_pre and/or relu(out) to out_post.
+constexpr int kMaxDevices = 64;  // per-device caches (kernel attributes, SM counts)
+
+// conv_igemm2.cu: persistent, tap-reusing tcgen05 implicit-GEMM convolution ----------------------
+// out = gate .* (alpha * conv(x, w) + bias) + add; writes out_pre and / or relu(out) to out_post.
 // round_flags: bit 0 = store out_pre rounded to tf32, bit 1 = store out_post rounded to tf32.
-// block_n / th / tw <= 0 select the heuristics.
-int conv_igemm_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
-                      const float* bias, const float* alpha, const float* mask_src,
-                      const float* add_src, float* out_pre, float* out_post, int round_flags,
-                      int block_n, int th, int tw, cudaStream_t stream);
+// N == 16 writes NCHW 3-channel planes (conv1_1 input gradient).  force_* <= 0 select the rule table.
+struct ConvArgs {
+  const float* x = nullptr;
+  const float* w_packed = nullptr;
+  int H = 0, W = 0, C = 0, N = 0, taps = 9;
+  const float* bias = nullptr;
+  const float* alpha = nullptr;         // device scalar
+  const float* mask_src = nullptr;      // fp32 ReLU gate source (x > 0)
+  const float* add_src = nullptr;
+  float* out_pre = nullptr;
+  float* out_post = nullptr;
+  int round_flags = 0;
+  float* out_nchw3 = nullptr;
+  float* out_pool = nullptr;            // fused 2x2 max pool of the post-ReLU output
+  unsigned* out_bits = nullptr;         // [H][W][N/32] sign bits of the post-ReLU output
+  unsigned* out_code = nullptr;         // [H/2][W/2][N/8] pool argmax + gate nibbles
+  const unsigned* mask_bits = nullptr;  // ReLU gate as bits (instead of mask_src)
+  const unsigned* unpool_code = nullptr;  // route the result through the 2x2 pool backward
+  int H2 = 0, W2 = 0;                   // un-pooled output size (unpool_code)
+  int force_n = 0, force_mh = 0, force_tw = 0;
+};
+int conv_igemm2_launch(const ConvArgs& args, cudaStream_t stream);
 
-// conv_igemm2.cu (persistent, tap-reusing version; N == 16 writes NCHW 3-channel planes) ---------
-int conv_igemm2_launch(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
-                       const float* bias, const float* alpha, const float* mask_src,
-                       const float* add_src, float* out_pre, float* out_post, int round_flags,
-                       float* out_nchw3, int force_n, int force_mh, int force_tw,
-                       cudaStream_t stream, float* out_pool = nullptr);
-
-// pair_mode -1: built-in rule table; 0: single-CTA tiles only; 1: CTA pairs (cta_group::2) wherever
-// legal.  a_stages / b_stages / tps > 0 override the ring depths and weight taps per stage.
+// Thread-local tile-policy overrides (tests and sweeps).  pair_mode -1: built-in rule table; 0:
+// single-CTA tiles only; 1: CTA pairs (cta_group::2) wherever legal.  a_stages / b_stages / tps > 0
+// override the ring depths and weight taps per stage.
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps);
 
 // gram.cu ---------------------------------------------------------------------------------
@@ -35,8 +48,8 @@ int gram_from_r_launch(const float* r, int C, double n_total, const float* targe
 
 // conv_direct.cu --------------------------------------------------------------------------
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
-                          int Cout, float* out_pre, float* out_post, int round_pre,
-                          cudaStream_t stream);
+                          int Cout, float* out_pre, float* out_post, unsigned* out_bits,
+                          int round_pre, cudaStream_t stream);
 int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
                             float* dimg_nchw, cudaStream_t stream);
 int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
@@ -80,5 +93,8 @@ int image_from_u8_launch(const unsigned char* hwc, int H, int W, int normalize, 
 int nchw_to_nhwc_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);
 int nhwc_to_nchw_launch(const float* src, int C, int H, int W, float* dst, cudaStream_t stream);
 int finite_flags_launch(const float* vals, int n, int* flags, cudaStream_t stream);
+int step_scores_launch(const float* losses, int n_style, int n_content, float style_w,
+                       float content_w, float* scores3, float* loss_ring, int* finite_ring,
+                       int capacity, int* counter, cudaStream_t stream);
 
 }  // namespace stv

@@ -20,6 +20,11 @@ from . import _native as nat
 from . import ops
 
 
+# Default of VggLossEngine.compact_backward for engines created from now on (A/B measurements flip it
+# before building a model).
+DEFAULT_COMPACT_BACKWARD = True
+
+
 @dataclass
 class _Stage:
     conv_idx: int
@@ -46,6 +51,8 @@ class _Workspace:
     d_y: list[torch.Tensor | None] = field(default_factory=list)
     d_post: list[torch.Tensor | None] = field(default_factory=list)
     d_pool: list[torch.Tensor | None] = field(default_factory=list)
+    bits: list[torch.Tensor | None] = field(default_factory=list)   # ReLU sign bits (int32 words)
+    code: list[torch.Tensor | None] = field(default_factory=list)   # pool argmax + gate nibbles
     gram_ws: list[torch.Tensor] = field(default_factory=list)
     s_mat: list[torch.Tensor] = field(default_factory=list)
     losses: torch.Tensor | None = None
@@ -74,6 +81,12 @@ class VggLossEngine:
         # overlap the tensor-core work (the fork/join structure is preserved by CUDA-graph capture).
         self._side = torch.cuda.Stream(device=device)
         self.overlap_losses = True
+        # Backward bookkeeping as bits instead of fp32 re-reads: the forward epilogues record the ReLU
+        # sign bits (1 bit / element) and the pool argmax + gate (4 bits / pooled element); the dgrad
+        # epilogues gate from the bits and route pooled gradients themselves (no pool-backward
+        # kernel, no full-resolution activation kept for pooled layers).  False = fp32 re-reads, kept
+        # for A/B measurements; stages whose ReLU / pool output is tapped by a loss always use those.
+        self.compact_backward = DEFAULT_COMPACT_BACKWARD
 
     # ------------------------------------------------------------------ program construction
     def _build_stages(self, layers: list[nn.Module]) -> list[_Stage]:
@@ -151,11 +164,16 @@ class VggLossEngine:
                 ws.nbytes += t.numel() * 4
                 return t
 
-            for st, (h, w) in zip(self.stages, ws.hw):
+            for s, (st, (h, w)) in enumerate(zip(self.stages, ws.hw)):
                 need_pre = st.conv_idx in self._tapped or st.relu_idx is None
                 ws.pre.append(buf(h, w, st.cout) if need_pre else None)
-                ws.post.append(buf(h, w, st.cout) if st.relu_idx is not None else None)
+                unpool = self._uses_unpool(s)
+                ws.post.append(buf(h, w, st.cout) if st.relu_idx is not None and not unpool
+                               else None)
                 ws.pool.append(buf(h // 2, w // 2, st.cout) if st.pool_idx is not None else None)
+                ws.bits.append(ops.relu_bits_buffer(h, w, st.cout, dev)
+                               if self._uses_bits(s) else None)
+                ws.code.append(ops.pool_code_buffer(h, w, st.cout, dev) if unpool else None)
                 ws.d_y.append(None)
                 ws.d_post.append(None)
                 ws.d_pool.append(None)
@@ -171,15 +189,31 @@ class VggLossEngine:
         if with_grad and ws.grad_img is None:
             dev = self.device
             for s, (st, (h, w)) in enumerate(zip(self.stages, ws.hw)):
-                ws.d_y[s] = torch.empty(h, w, st.cout, device=dev, dtype=torch.float32)
+                # zero-filled: the un-pooling dgrad never writes a last row / column that floor-mode
+                # pooling dropped (its gradient is zero)
+                ws.d_y[s] = torch.zeros(h, w, st.cout, device=dev, dtype=torch.float32)
                 ws.nbytes += ws.d_y[s].numel() * 4
-                if st.pool_idx is not None:
+                if st.pool_idx is not None and not self._uses_unpool(s):
                     ws.d_pool[s] = torch.empty(h // 2, w // 2, st.cout, device=dev,
                                                dtype=torch.float32)
                 if st.relu_idx is not None and st.relu_idx in self._tapped:
                     ws.d_post[s] = torch.empty(h, w, st.cout, device=dev, dtype=torch.float32)
             ws.grad_img = torch.empty(1, 3, height, width, device=dev, dtype=torch.float32)
         return ws
+
+    def _uses_bits(self, s: int) -> bool:
+        """Stage ``s`` = conv -> ReLU (no pool, ReLU output not tapped) feeding another conv: its ReLU
+        backward is applied from recorded sign bits in the next layer's dgrad epilogue."""
+        st = self.stages[s]
+        return (self.compact_backward and st.relu_idx is not None and st.pool_idx is None
+                and st.relu_idx not in self._tapped and s + 1 < len(self.stages))
+
+    def _uses_unpool(self, s: int) -> bool:
+        """Stage ``s`` = conv -> ReLU -> pool with no loss tap, feeding another conv: the pool + ReLU
+        backward is applied from recorded codes in the next layer's dgrad epilogue."""
+        st = self.stages[s]
+        return (self.compact_backward and s > 0 and st.pool_idx is not None
+                and not self._stage_taps(st) and s + 1 < len(self.stages))
 
     def grad_buffer(self, height: int, width: int) -> torch.Tensor:
         """The NCHW buffer ``backward_losses`` writes for this image size."""
@@ -231,15 +265,22 @@ class VggLossEngine:
         for s, st in enumerate(self.stages):
             if s == 0:
                 ops.conv3x3_first_fwd(x, st.weight, st.bias, ws.pre[0], ws.post[0],
-                                      round_pre=self._round_pre(st))
+                                      round_pre=self._round_pre(st), out_bits=ws.bits[0])
+            elif ws.code[s] is not None:
+                # conv + ReLU + MaxPool2d in one launch; only the pooled map and the 4-bit pool
+                # codes reach memory (the backward pass needs nothing else of this layer)
+                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], None,
+                                round_pre=self._round_pre(st), out_pool=ws.pool[s],
+                                out_code=ws.code[s])
             else:
                 # the MaxPool2d after conv1_2 / 2_2 / 3_4 / 4_4 is computed in the conv epilogue
                 fused_pool = ws.pool[s] if st.pool_idx is not None and ws.post[s] is not None else None
                 ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s],
-                                round_pre=self._round_pre(st), out_pool=fused_pool)
+                                round_pre=self._round_pre(st), out_pool=fused_pool,
+                                out_bits=ws.bits[s] if fused_pool is None else None)
             cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
             if st.pool_idx is not None:
-                if s == 0 or ws.post[s] is None:
+                if ws.code[s] is None and (s == 0 or ws.post[s] is None):
                     ops.maxpool2_fwd(ws.post[s], ws.pool[s])
                 cur = ws.pool[s]
             if after_stage is not None:
@@ -386,7 +427,10 @@ class VggLossEngine:
             down = self.stages[s + 1] if s + 1 < n else None
             d_y = ws.d_y[s]
             tap_post = st.relu_idx is not None and st.relu_idx in self._tapped
-            if st.pool_idx is not None:
+            if ws.code[s] is not None:
+                # dgrad of the next conv at pooled resolution, pool + ReLU backward in its epilogue
+                ops.conv3x3_dgrad_unpool(ws.d_y[s + 1], down.w_dgrad, ws.code[s], d_y)
+            elif st.pool_idx is not None:
                 d_pool = ws.d_pool[s]
                 acc = self._tap_grads(ws, st.pool_idx, ws.pool[s], d_pool, grad_w, False)
                 if down is not None:
@@ -415,8 +459,12 @@ class VggLossEngine:
                     else:
                         acc = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
                     # ReLU backward mask fused into the dgrad epilogue
-                    ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_src=ws.post[s],
-                                      accumulate=acc)
+                    if ws.bits[s] is not None:
+                        ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_bits=ws.bits[s],
+                                          accumulate=acc)
+                    else:
+                        ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_src=ws.post[s],
+                                          accumulate=acc)
             elif s in early:
                 main.wait_event(early[s])
             else:

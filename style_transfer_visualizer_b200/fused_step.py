@@ -22,7 +22,7 @@ class FusedStep:
 
     @classmethod
     def try_create(cls, model: object, x: torch.Tensor, optimizer: object, style_w: float,
-                   content_w: float) -> "FusedStep | None":
+                   content_w: float, *, record_capacity: int = 0) -> "FusedStep | None":
         if not isinstance(model, StyleContentModel):
             return None
         is_lbfgs = isinstance(optimizer, FusedLBFGS) and \
@@ -36,10 +36,11 @@ class FusedStep:
         params = [p for g in optimizer.param_groups for p in g["params"]]
         if len(params) != 1 or params[0] is not x:
             return None
-        return cls(model, x, optimizer, style_w, content_w)
+        return cls(model, x, optimizer, style_w, content_w, record_capacity=record_capacity)
 
     def __init__(self, model: StyleContentModel, x: torch.Tensor,
-                 optimizer: "FusedAdam | FusedLBFGS", style_w: float, content_w: float) -> None:
+                 optimizer: "FusedAdam | FusedLBFGS", style_w: float, content_w: float, *,
+                 record_capacity: int = 0) -> None:
         self.x = x
         self.optimizer = optimizer
         self.engine = model.engine_for(x.device)
@@ -71,23 +72,32 @@ class FusedStep:
             optimizer._device_state()  # noqa: SLF001  (history buffers allocated before capture)
         self.state = state
         self.scores = torch.zeros(3, device=dev, dtype=torch.float32)   # style, content, total
-        self._tmp = torch.zeros(2, device=dev, dtype=torch.float32)
+        # Per-step records written INSIDE the graph at a device-side step counter (reference
+        # optimization.py:375-391 finiteness checks, :402-422 loss recording): the runner reads rows
+        # at its logging cadence instead of launching bookkeeping kernels every step.
+        self.record_capacity = int(record_capacity)
+        self.loss_ring: torch.Tensor | None = None      # [capacity, 3]
+        self.finite_ring: torch.Tensor | None = None    # [capacity] int32 bit flags
+        self.record_counter: torch.Tensor | None = None  # [1] int32: rows written so far
+        if self.record_capacity > 0:
+            self.loss_ring = torch.zeros(self.record_capacity, 3, device=dev, dtype=torch.float32)
+            self.finite_ring = torch.zeros(self.record_capacity, device=dev, dtype=torch.int32)
+            self.record_counter = torch.zeros(1, device=dev, dtype=torch.int32)
         self.height, self.width = int(x.shape[2]), int(x.shape[3])
         self.graph: torch.cuda.CUDAGraph | None = None
         self.kernel_launches = 0
 
     def _forward_backward(self) -> torch.Tensor:
         losses, _gen = self.engine.forward_losses(self.x.detach())
-        ns = self.n_style
-        torch.sum(losses[:ns], dim=0, out=self.scores[0])
-        torch.sum(losses[ns:], dim=0, out=self.scores[1])
-        torch.mul(self.scores[0], self.style_w, out=self._tmp[0])
-        torch.mul(self.scores[1], self.content_w, out=self._tmp[1])
-        torch.add(self._tmp[0], self._tmp[1], out=self.scores[2])
+        self._losses = losses
         return self.engine.backward_losses(self.height, self.width, self.grad_w)
 
     def _body(self) -> None:
         grad = self._forward_backward()
+        # weighted total, finiteness flags and the history row: one single-thread kernel
+        ops.step_scores(self._losses, self.n_style, self.n_content, self.style_w, self.content_w,
+                        self.scores, loss_ring=self.loss_ring, finite_ring=self.finite_ring,
+                        counter=self.record_counter)
         if self.is_adam:
             ops.adam_step_dev(self.x.detach(), grad, self.state["exp_avg"],
                               self.state["exp_avg_sq"], self.adam_state, lr=self.lr,

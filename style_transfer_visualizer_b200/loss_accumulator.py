@@ -47,6 +47,23 @@ class LossAccumulator:
         self._records = 0       # total writes ever
         self._pending: tuple[int, torch.Tensor, torch.Tensor, torch.Tensor] | None = None
         self._last_logged: LoggedLoss | None = None
+        # rows [capacity, 3] written by the captured step graph itself (see adopt_device_rows)
+        self._device_rows: torch.Tensor | None = None
+
+    def adopt_device_rows(self, rows: torch.Tensor) -> None:
+        """Use ``rows`` ``[capacity, 3]`` as the history ring: the producer (the captured step graph,
+        ``stv_step_scores``) writes row ``k % capacity`` for its k-th step by itself, so
+        ``accumulate`` only does host bookkeeping -- no per-step device work at all.  Must be called
+        before the first ``accumulate``; the producer's row counter must start at zero with it."""
+        if self._records:
+            msg = "adopt_device_rows must precede the first accumulate()"
+            raise RuntimeError(msg)
+        if rows.dim() != 2 or rows.shape[1] != 3 or rows.shape[0] != self._history_capacity:
+            msg = (f"device rows must have shape [{self._history_capacity}, 3], "
+                   f"got {tuple(rows.shape)}")
+            raise ValueError(msg)
+        self._device_rows = rows
+        self._ring = None
 
     @property
     def capacity(self) -> int:
@@ -66,7 +83,9 @@ class LossAccumulator:
         """Record one step; return host scalars only on ``log_every`` steps (or ``force``)."""
         vals = (style_loss.detach(), content_loss.detach(), total_loss.detach())
         self._pending = (step_idx, *vals)
-        if self._track_history:
+        if self._device_rows is not None:
+            self._advance()  # the row is already on the device
+        elif self._track_history:
             self._push(vals)
         if force or step_idx % self._log_every == 0:
             return self._sync_pending()
@@ -77,12 +96,13 @@ class LossAccumulator:
 
     def export_history(self) -> dict[str, list[float]]:
         """Retained history, oldest first, as plain lists."""
-        if not self._track_history or self._filled == 0 or self._ring is None:
+        ring = self._device_rows.t() if self._device_rows is not None else self._ring
+        if not self._track_history or self._filled == 0 or ring is None:
             return {name: [] for name in _NAMES}
         start = (self._cursor - self._filled) % self._history_capacity
-        order = (torch.arange(self._filled, device=self._ring.device) + start) \
+        order = (torch.arange(self._filled, device=ring.device) + start) \
             % self._history_capacity
-        window = self._ring.index_select(1, order).cpu()
+        window = ring.index_select(1, order).cpu()
         return {name: window[row].tolist() for row, name in enumerate(_NAMES)}
 
     def _push(self, vals: tuple[torch.Tensor, torch.Tensor, torch.Tensor]) -> None:
@@ -92,7 +112,10 @@ class LossAccumulator:
         slot = self._cursor
         for row, val in enumerate(vals):
             self._ring[row, slot] = val.to(dtype=self._buffer_dtype, device=self._device)
-        self._cursor = (slot + 1) % self._history_capacity
+        self._advance()
+
+    def _advance(self) -> None:
+        self._cursor = (self._cursor + 1) % self._history_capacity
         self._filled = min(self._filled + 1, self._history_capacity)
         self._records += 1
 
@@ -100,9 +123,15 @@ class LossAccumulator:
         if self._pending is None:
             return None
         step, style, content, total = self._pending
-        logged = LoggedLoss(step=step, style_loss=self._to_float(style),
-                            content_loss=self._to_float(content),
-                            total_loss=self._to_float(total))
+        if self._device_rows is not None:
+            # the three scalars of the row just written, in ONE device->host copy
+            row = self._device_rows[(self._cursor - 1) % self._history_capacity].tolist()
+            logged = LoggedLoss(step=step, style_loss=float(row[0]), content_loss=float(row[1]),
+                                total_loss=float(row[2]))
+        else:
+            logged = LoggedLoss(step=step, style_loss=self._to_float(style),
+                                content_loss=self._to_float(content),
+                                total_loss=self._to_float(total))
         self._last_logged = logged
         return logged
 

@@ -33,38 +33,84 @@ def pack_conv_weights(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return wf, wd
 
 
+def relu_bits_buffer(h: int, w: int, channels: int, device: torch.device) -> torch.Tensor:
+    """``[H, W, C/32]`` int32 words: sign bits of a post-ReLU activation (``stv_conv3x3_fwd_bits``)."""
+    return torch.empty(h, w, channels // 32, device=device, dtype=torch.int32)
+
+
+def pool_code_buffer(h: int, w: int, channels: int, device: torch.device) -> torch.Tensor:
+    """``[H/2, W/2, C/8]`` int32 words: pool argmax + ReLU gate nibbles (``stv_conv3x3_fwd_pool_code``)."""
+    return torch.empty(h // 2, w // 2, channels // 8, device=device, dtype=torch.int32)
+
+
 def conv3x3_first_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
                       out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
-                      round_pre: bool = False) -> None:
+                      round_pre: bool = False, out_bits: torch.Tensor | None = None) -> None:
     _chk(img, "img")
     h, wd = img.shape[-2], img.shape[-1]
+    if out_bits is not None:
+        nat.call("stv_conv3x3_first_fwd_bits", nat.ptr(img), nat.ptr(w), nat.ptr(bias), h, wd,
+                 w.shape[0], nat.ptr(out_pre), nat.ptr(out_post), nat.ptr(out_bits),
+                 int(round_pre), _s(img))
+        return
     nat.call("stv_conv3x3_first_fwd", nat.ptr(img), nat.ptr(w), nat.ptr(bias), h, wd, w.shape[0],
              nat.ptr(out_pre), nat.ptr(out_post), int(round_pre), _s(img))
 
 
-def conv3x3_fwd(x: torch.Tensor, w_fwd: torch.Tensor, bias: torch.Tensor | None,
+def conv3x3_fwd(x: torch.Tensor, w_fwd: torch.Tensor, bias: torch.Tensor | None,  # noqa: PLR0913
                 out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
-                round_pre: bool = False, out_pool: torch.Tensor | None = None) -> None:
+                round_pre: bool = False, out_pool: torch.Tensor | None = None,
+                out_bits: torch.Tensor | None = None,
+                out_code: torch.Tensor | None = None) -> None:
     """3x3 conv + bias (+ReLU into out_post); with ``out_pool`` also the 2x2 max pool of out_post,
-    computed in the conv epilogue (``stv_conv3x3_fwd_pool``)."""
+    computed in the conv epilogue (``stv_conv3x3_fwd_pool``).  ``out_bits`` / ``out_code`` record the
+    ReLU sign bits / the pool argmax codes for the backward pass."""
     _chk(x, "x")
     h, wd, cin = x.shape
     cout = w_fwd.shape[1]
+    if out_code is not None:
+        nat.call("stv_conv3x3_fwd_pool_code", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin,
+                 cout, nat.ptr(out_pre), nat.ptr(out_post), nat.ptr(out_pool), nat.ptr(out_code),
+                 int(round_pre), _s(x))
+        return
     if out_pool is not None:
         nat.call("stv_conv3x3_fwd_pool", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
                  nat.ptr(out_pre), nat.ptr(out_post), nat.ptr(out_pool), int(round_pre), _s(x))
+        return
+    if out_bits is not None:
+        nat.call("stv_conv3x3_fwd_bits", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
+                 nat.ptr(out_pre), nat.ptr(out_post), nat.ptr(out_bits), int(round_pre), _s(x))
         return
     nat.call("stv_conv3x3_fwd", nat.ptr(x), nat.ptr(w_fwd), nat.ptr(bias), h, wd, cin, cout,
              nat.ptr(out_pre), nat.ptr(out_post), int(round_pre), _s(x))
 
 
 def conv3x3_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, dx: torch.Tensor,
-                  relu_src: torch.Tensor | None = None, *, accumulate: bool = False) -> None:
+                  relu_src: torch.Tensor | None = None, *, accumulate: bool = False,
+                  relu_bits: torch.Tensor | None = None) -> None:
+    """Input gradient of a 3x3 conv; the ReLU gate comes from ``relu_src`` (fp32 activation) or from
+    ``relu_bits`` (its recorded sign bits)."""
     _chk(dy, "dy")
     h, wd, cout = dy.shape
     cin = w_dgrad.shape[1]
+    if relu_bits is not None:
+        nat.call("stv_conv3x3_dgrad_bits", nat.ptr(dy), nat.ptr(w_dgrad), h, wd, cout, cin,
+                 nat.ptr(relu_bits), int(accumulate), nat.ptr(dx), _s(dy))
+        return
     nat.call("stv_conv3x3_dgrad", nat.ptr(dy), nat.ptr(w_dgrad), h, wd, cout, cin,
              nat.ptr(relu_src), int(accumulate), nat.ptr(dx), _s(dy))
+
+
+def conv3x3_dgrad_unpool(dy: torch.Tensor, w_dgrad: torch.Tensor, pool_code: torch.Tensor,
+                         dx: torch.Tensor) -> None:
+    """dgrad at pooled resolution fused with the 2x2 max-pool + ReLU backward: ``dx`` ``[H2, W2, Cin]``
+    is the gradient at the resolution before the pool (``stv_conv3x3_dgrad_unpool``)."""
+    _chk(dy, "dy")
+    h, wd, cout = dy.shape
+    cin = w_dgrad.shape[1]
+    h2, w2 = dx.shape[0], dx.shape[1]
+    nat.call("stv_conv3x3_dgrad_unpool", nat.ptr(dy), nat.ptr(w_dgrad), h, wd, cout, cin,
+             nat.ptr(pool_code), h2, w2, nat.ptr(dx), _s(dy))
 
 
 def conv3x3_first_dgrad(dy: torch.Tensor, w: torch.Tensor, dimg: torch.Tensor) -> None:
@@ -251,17 +297,17 @@ def finite_flags(vals: torch.Tensor, flags: torch.Tensor) -> None:
     nat.call("stv_finite_flags", nat.ptr(vals), vals.numel(), nat.ptr(flags), _s(vals))
 
 
-def conv_igemm_ex(x: torch.Tensor, w_packed: torch.Tensor, *, taps: int,  # noqa: PLR0913
-                  bias: torch.Tensor | None = None, alpha: torch.Tensor | None = None,
-                  mask_src: torch.Tensor | None = None, add_src: torch.Tensor | None = None,
-                  out_pre: torch.Tensor | None = None, out_post: torch.Tensor | None = None,
-                  block_n: int = 0, th: int = 0, tw: int = 0) -> None:
-    """Test hook: the tensor-core conv with explicit tile selection."""
-    h, wd, c = x.shape
-    n = w_packed.shape[-2]
-    nat.call("stv_conv_igemm_ex", nat.ptr(x), nat.ptr(w_packed), h, wd, c, n, taps, nat.ptr(bias),
-             nat.ptr(alpha), nat.ptr(mask_src), nat.ptr(add_src), nat.ptr(out_pre),
-             nat.ptr(out_post), block_n, th, tw, _s(x))
+def step_scores(losses: torch.Tensor, n_style: int, n_content: int, style_w: float,  # noqa: PLR0913
+                content_w: float, scores3: torch.Tensor, *, loss_ring: torch.Tensor | None = None,
+                finite_ring: torch.Tensor | None = None,
+                counter: torch.Tensor | None = None) -> None:
+    """{style, content, total} of one step, appended to device rings at a device step counter
+    (``stv_step_scores``)."""
+    capacity = int(loss_ring.shape[0]) if loss_ring is not None else \
+        (int(finite_ring.shape[0]) if finite_ring is not None else 0)
+    nat.call("stv_step_scores", nat.ptr(losses), n_style, n_content, float(style_w),
+             float(content_w), nat.ptr(scores3), nat.ptr(loss_ring), nat.ptr(finite_ring), capacity,
+             nat.ptr(counter), _s(losses))
 
 
 def conv_igemm2_ex(x: torch.Tensor, w_packed: torch.Tensor, *, taps: int,  # noqa: PLR0913

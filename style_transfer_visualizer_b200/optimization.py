@@ -139,8 +139,11 @@ class OptimizationRunner:
         self._async_frames = on_cuda if async_frames is None else (async_frames and on_cuda)
         self._readback: stv_image_io.FrameReadback | None = None
         self._lazy_finite = on_cuda
-        self._finite_ring: torch.Tensor | None = None
+        self._finite_ring: torch.Tensor | None = None     # [window] int32 bit flags (eager steps)
+        self._finite_vals: torch.Tensor | None = None     # [3] staging for stv_finite_flags
         self._finite_steps: list[int] = []
+        self._graph_records = False   # finiteness + history rows written inside the step graph
+        self._graph_rows_written = 0
         self._use_cuda_graph = use_cuda_graph
         self._fused = None  # FusedStep, built lazily in run()
         self.frames_emitted = 0
@@ -184,6 +187,16 @@ class OptimizationRunner:
                 self._pending_step_tensors = None
             self._drain_frames()
             self._flush_finite_checks()
+        except BaseException:
+            # A failing or interrupted run still owes the sinks the frames already submitted and the
+            # log the deferred "Non-finite ..." warnings -- on CUDA often the only explanation of the
+            # failure (the reference emitted them synchronously).  Best effort: never mask the error.
+            for late in (self._drain_frames, self._flush_finite_checks):
+                try:
+                    late()
+                except Exception:  # noqa: BLE001, S110
+                    pass
+            raise
         finally:
             self._cleanup()
 
@@ -333,17 +346,25 @@ class OptimizationRunner:
         """Warn when a recorded loss is non-finite (same messages as the reference,
         optimization.py:375-400).  On CUDA the three flags are written to a device ring and the
         warnings are emitted at the next logging sync instead of stalling every closure."""
-        if self._lazy_finite and style_score.is_cuda:
+        if self._graph_records:
+            # the captured graph already wrote this step's flags (stv_step_scores) to its ring
+            if len(self._finite_steps) == self._fused.record_capacity:
+                self._flush_finite_checks()
+            self._finite_steps.append(step_idx)
+        elif self._lazy_finite and style_score.is_cuda:
+            from . import ops
+
             if self._finite_ring is None:
                 window = max(1, min(self.config.output.log_every, 1024))
                 self._finite_ring = torch.zeros(window, 3, device=style_score.device,
-                                                dtype=torch.bool)
+                                                dtype=torch.int32)
+                self._finite_vals = torch.zeros(3, device=style_score.device, dtype=torch.float32)
             if len(self._finite_steps) == self._finite_ring.shape[0]:
                 self._flush_finite_checks()
             row = len(self._finite_steps)
-            vals = torch.stack((style_score.detach(), content_score.detach(),
-                                total_loss.detach()))
-            torch.logical_not(torch.isfinite(vals), out=self._finite_ring[row])
+            torch.stack((style_score.detach(), content_score.detach(), total_loss.detach()),
+                        out=self._finite_vals)
+            ops.finite_flags(self._finite_vals, self._finite_ring[row])  # flags |= !isfinite
             self._finite_steps.append(step_idx)
         else:
             for which, val in enumerate((style_score, content_score, total_loss)):
@@ -357,12 +378,27 @@ class OptimizationRunner:
 
     def _flush_finite_checks(self) -> None:
         """Read the pending finiteness flags (one small D2H) and emit the warnings in order."""
-        if not self._finite_steps or self._finite_ring is None:
+        if not self._finite_steps:
             return
-        flags = self._finite_ring[:len(self._finite_steps)].cpu()
+        n = len(self._finite_steps)
+        if self._graph_records:
+            fused = self._fused
+            cap = fused.record_capacity
+            ring = fused.finite_ring.cpu()
+            # the graph has written rows 0 .. self._step_records - 1 (mod capacity); the pending
+            # steps are the last n of them
+            last = self._graph_rows_written
+            rows = [int(ring[(last - n + i) % cap]) for i in range(n)]
+            flags = [[bool(r & 1), bool(r & 2), bool(r & 4)] for r in rows]
+        elif self._finite_ring is not None:
+            host = self._finite_ring[:n].cpu()
+            flags = [[bool(host[r, w]) for w in range(3)] for r in range(n)]
+            self._finite_ring.zero_()
+        else:
+            return
         for row, step_idx in enumerate(self._finite_steps):
             for which in range(3):
-                if bool(flags[row, which]):
+                if flags[row][which]:
                     self._warn_non_finite(which, step_idx)
         self._finite_steps.clear()
 
@@ -472,9 +508,19 @@ class OptimizationRunner:
             return
         from .fused_step import FusedStep
 
+        acc = self._loss_accumulator
+        capacity = acc.capacity if acc is not None else min(self.total_steps,
+                                                            DEFAULT_HISTORY_CAPACITY)
         self._fused = FusedStep.try_create(self.model, self.input_img, self.optimizer,
                                            self.config.optimization.style_w,
-                                           self.config.optimization.content_w)
+                                           self.config.optimization.content_w,
+                                           record_capacity=capacity)
+        if self._fused is not None and self._step_index == 0:
+            # history rows and finiteness flags come from the graph itself from now on
+            self._graph_records = True
+            self._graph_rows_written = 0
+            if acc is not None:
+                acc.adopt_device_rows(self._fused.loss_ring)
         if self._fused is None and self._use_cuda_graph:
             msg = ("use_cuda_graph=True needs this package's StyleContentModel with targets set "
                    "and a FusedAdam or FusedLBFGS(max_iter=1) optimiser on the image")
@@ -483,6 +529,8 @@ class OptimizationRunner:
     def _fused_step(self, step_idx: int) -> None:
         self._closure_calls += 1
         style_score, content_score, loss = self._fused.step()
+        if self._graph_records:
+            self._graph_rows_written += 1
         self._check_finite(style_score, content_score, loss, step_idx)
         self._pending_step_tensors = StepTensors(
             step=step_idx, style_score=style_score, content_score=content_score, total_loss=loss)

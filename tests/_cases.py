@@ -50,12 +50,20 @@ def initial_image(cfg: dict, content: torch.Tensor, init: torch.Tensor | None) -
     raise ValueError(cfg["init"])
 
 
+def sample_stride(cfg: dict) -> int:
+    """Spatial stride of the image-shaped samples a fixture stores (1 = everything); must mirror
+    oracle/make_golden.py."""
+    px = cfg["h"] * cfg["w"]
+    if px > 1024 * 1024:
+        return 8
+    return 4 if px > 128 * 128 else 1
+
+
 def subsample_like_golden(cfg: dict, t: torch.Tensor | np.ndarray) -> np.ndarray:
-    """Big cases store [..., ::4, ::4] samples of image-shaped tensors."""
+    """Big cases store strided samples [..., ::k, ::k] of image-shaped tensors."""
     arr = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t
-    if cfg["h"] * cfg["w"] > 128 * 128:
-        return np.ascontiguousarray(arr[..., ::4, ::4])
-    return arr
+    k = sample_stride(cfg)
+    return np.ascontiguousarray(arr[..., ::k, ::k]) if k > 1 else arr
 
 
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:

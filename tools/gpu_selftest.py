@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-CASES = ["elementwise", "conv", "conv2", "conv_variants", "gram", "perf"]
+CASES = ["elementwise", "conv", "conv2", "conv_variants", "conv_compact", "gram", "perf"]
 
 
 def rel_l2(a, b):  # noqa: ANN001, ANN201
@@ -235,8 +235,8 @@ def case_conv() -> bool:
         ref = nhwc(F.conv2d(x, wt, b, padding=1))
         pre = torch.full((h, w, cout), float("nan"), device=dev)
         post = torch.full((h, w, cout), float("nan"), device=dev)
-        ops.conv_igemm_ex(nhwc(x), wf, taps=9, bias=b, out_pre=pre, out_post=post, block_n=bn,
-                          th=th, tw=tw)
+        ops.conv_igemm2_ex(nhwc(x), wf, taps=9, bias=b, out_pre=pre, out_post=post, block_n=bn,
+                           tw=tw if tw in (8, 16, 32) else 0)
         torch.cuda.synchronize()
         tag = f"{h}x{w} {cin}->{cout} bn={bn} patch={th}x{tw}"
         ok &= report(f"igemm fwd pre  {tag}", rel_l2(pre, ref), 2e-3)
@@ -395,6 +395,136 @@ def case_conv_variants() -> bool:
     return ok
 
 
+def case_conv_compact() -> bool:
+    """Backward bookkeeping as bits: ReLU sign bits / pool codes recorded by the forward epilogues,
+    consumed by the dgrad epilogues.  Everything here must be BIT-IDENTICAL to the fp32-re-reading
+    path (same accumulators, same arithmetic; only where the gate comes from differs)."""
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    ok = True
+
+    def unpack_bits(bits: torch.Tensor, c: int) -> torch.Tensor:
+        """[H, W, C/32] int32 -> [H, W, C] bool."""
+        sh = torch.arange(32, device=bits.device, dtype=torch.int32)
+        return ((bits.unsqueeze(-1) >> sh) & 1).reshape(*bits.shape[:2], c).bool()
+
+    def unpack_code(code: torch.Tensor, c: int) -> torch.Tensor:
+        """[Ho, Wo, C/8] int32 -> [Ho, Wo, C] int (nibbles)."""
+        sh = torch.arange(0, 32, 4, device=code.device, dtype=torch.int32)
+        return ((code.unsqueeze(-1) >> sh) & 15).reshape(*code.shape[:2], c)
+
+    # first layer: bits of conv1_1's post
+    for (hh, ww) in [(64, 64), (33, 47), (70, 94)]:
+        img = torch.randn(1, 3, hh, ww, device=dev, generator=g)
+        w1 = torch.randn(64, 3, 3, 3, device=dev, generator=g) * 0.2
+        b1 = torch.randn(64, device=dev, generator=g) * 0.1
+        pre = torch.empty(hh, ww, 64, device=dev)
+        post = torch.empty(hh, ww, 64, device=dev)
+        pre2 = torch.empty_like(pre)
+        post2 = torch.empty_like(post)
+        bits = torch.full((hh, ww, 2), -1, device=dev, dtype=torch.int32)
+        ops.conv3x3_first_fwd(img, w1, b1, pre, post)
+        ops.conv3x3_first_fwd(img, w1, b1, pre2, post2, out_bits=bits)
+        same = torch.equal(pre, pre2) and torch.equal(post, post2) and \
+            torch.equal(unpack_bits(bits, 64), post > 0)
+        ok &= report(f"first fwd + sign bits {hh}x{ww}", 0.0 if same else 1.0, 0.0)
+
+    for (hh, ww, ci, co) in [(40, 56, 64, 64), (37, 53, 64, 128), (70, 94, 128, 128), (33, 47, 128, 256),
+                             (24, 40, 256, 256), (19, 8, 256, 512), (16, 16, 512, 512), (9, 11, 64, 64),
+                             (135, 240, 64, 64)]:
+        xx = torch.randn(hh, ww, ci, device=dev, generator=g)
+        wt = torch.randn(co, ci, 3, 3, device=dev, generator=g) * 0.05
+        wf, wd = ops.pack_conv_weights(wt)
+        bb = torch.randn(co, device=dev, generator=g) * 0.3
+        for pair_mode in (-1, 0, 1):
+            ops.conv_set_tuning(pair_mode)
+            tag = f"{hh}x{ww} {ci}->{co} pair_mode={pair_mode}"
+            # ---- forward: sign bits
+            post = torch.empty(hh, ww, co, device=dev)
+            post2 = torch.empty_like(post)
+            bits = torch.full((hh, ww, co // 32), -1, device=dev, dtype=torch.int32)
+            ops.conv3x3_fwd(xx, wf, bb, None, post)
+            ops.conv3x3_fwd(xx, wf, bb, None, post2, out_bits=bits)
+            same = torch.equal(post, post2) and torch.equal(unpack_bits(bits, co), post > 0)
+            ok &= report(f"fwd + sign bits {tag}", 0.0 if same else 1.0, 0.0)
+            # ---- forward: pool + codes, post not stored
+            ho, wo = hh // 2, ww // 2
+            pool = torch.full((ho, wo, co), float("nan"), device=dev)
+            code = torch.full((ho, wo, co // 8), -1, device=dev, dtype=torch.int32)
+            ops.conv3x3_fwd(xx, wf, bb, None, None, out_pool=pool, out_code=code)
+            pool_ref = torch.empty_like(pool)
+            ops.maxpool2_fwd(post, pool_ref)
+            win = post[:2 * ho, :2 * wo].reshape(ho, 2, wo, 2, co).permute(0, 2, 4, 1, 3) \
+                .reshape(ho, wo, co, 4)                       # window order a, b, d, e
+            k = torch.zeros(ho, wo, co, device=dev, dtype=torch.int64)
+            m = win[..., 0].clone()
+            for q in (1, 2, 3):
+                better = win[..., q] > m
+                k = torch.where(better, torch.full_like(k, q), k)
+                m = torch.where(better, win[..., q], m)
+            nib_ref = k + 4 * (m > 0)
+            same = torch.equal(pool, pool_ref) and torch.equal(unpack_code(code, co).long(), nib_ref)
+            ok &= report(f"fwd + pool + codes {tag}", 0.0 if same else 1.0, 0.0)
+            # ---- dgrad gated by bits == dgrad gated by the fp32 activation (layer gated: [hh,ww,ci])
+            dy = torch.randn(hh, ww, co, device=dev, generator=g)
+            act = torch.randn(hh, ww, ci, device=dev, generator=g).relu()
+            abits = torch.zeros(hh, ww, ci // 32, device=dev, dtype=torch.int32)
+            sh = torch.arange(32, device=dev, dtype=torch.int64)
+            packed = ((act > 0).reshape(hh, ww, ci // 32, 32).long() << sh).sum(-1)
+            abits.copy_(torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).int())
+            if ci % 64 == 0:
+                prev = torch.randn(hh, ww, ci, device=dev, generator=g)
+                for accumulate in (False, True):
+                    d_a = prev.clone()
+                    d_b = prev.clone()
+                    ops.conv3x3_dgrad(dy, wd, d_a, relu_src=act, accumulate=accumulate)
+                    ops.conv3x3_dgrad(dy, wd, d_b, relu_bits=abits, accumulate=accumulate)
+                    ok &= report(f"dgrad gate bits acc={int(accumulate)} {tag}",
+                                 0.0 if torch.equal(d_a, d_b) else 1.0, 0.0)
+        ops.conv_set_tuning()
+    # ---- dgrad fused with pool + ReLU backward == dgrad -> maxpool2_bwd(relu_mask); odd sizes: the
+    # dropped last row / column stays zero
+    for (h2, w2, cpool, cnext) in [(40, 56, 64, 128), (37, 53, 64, 128), (71, 95, 128, 256),
+                                   (33, 47, 256, 512), (16, 16, 512, 512), (135, 241, 64, 128)]:
+        ho, wo = h2 // 2, w2 // 2
+        post = torch.randn(h2, w2, cpool, device=dev, generator=g).relu()
+        post = torch.where(torch.rand(h2, w2, cpool, device=dev, generator=g) < 0.1,
+                           post.roll(1, 1), post)            # some exact ties inside windows
+        wt = torch.randn(cnext, cpool, 3, 3, device=dev, generator=g) * 0.05
+        _wf, wd = ops.pack_conv_weights(wt)
+        dy = torch.randn(ho, wo, cnext, device=dev, generator=g)
+        # codes from the reference definition (first maximum in scan order, gate = max > 0)
+        win = post[:2 * ho, :2 * wo].reshape(ho, 2, wo, 2, cpool).permute(0, 2, 4, 1, 3) \
+            .reshape(ho, wo, cpool, 4)
+        k = torch.zeros(ho, wo, cpool, device=dev, dtype=torch.int64)
+        m = win[..., 0].clone()
+        for q in (1, 2, 3):
+            better = win[..., q] > m
+            k = torch.where(better, torch.full_like(k, q), k)
+            m = torch.where(better, win[..., q], m)
+        nib = k + 4 * (m > 0)
+        sh4 = torch.arange(0, 32, 4, device=dev, dtype=torch.int64)
+        packed = (nib.reshape(ho, wo, cpool // 8, 8) << sh4).sum(-1)
+        code = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).int().contiguous()
+        for pair_mode in (-1, 0, 1):
+            ops.conv_set_tuning(pair_mode)
+            d_pool = torch.empty(ho, wo, cpool, device=dev)
+            ops.conv3x3_dgrad(dy, wd, d_pool)
+            want = torch.empty(h2, w2, cpool, device=dev)
+            ops.maxpool2_bwd(d_pool, post, want, relu_mask=True)
+            got = torch.zeros(h2, w2, cpool, device=dev)
+            ops.conv3x3_dgrad_unpool(dy, wd, code, got)
+            ok &= report(f"dgrad + unpool {h2}x{w2} {cnext}->{cpool} pair_mode={pair_mode}",
+                         0.0 if torch.equal(got, want) else 1.0, 0.0)
+        ops.conv_set_tuning()
+    torch.cuda.synchronize()
+    return ok
+
+
 def case_gram() -> bool:
     import torch
 
@@ -492,11 +622,6 @@ def case_perf() -> bool:
         flops = 2.0 * 9 * cin * cout * h * w
         ms = _time(lambda: ops.conv3x3_fwd(x, wf, b, None, post))  # noqa: B023
         line = f"PERF conv {h}x{w} {cin}->{cout}: auto {ms:.3f} ms {flops / ms / 1e9:.1f} TF/s"
-        for bn in (64, 128, 256):
-            if cout % bn:
-                continue
-            ms2 = _time(lambda: ops.conv_igemm_ex(x, wf, taps=9, bias=b, out_post=post, block_n=bn))  # noqa: B023
-            line += f" | v1 bn{bn} {flops / ms2 / 1e9:.0f}"
         for bn in (64, 128, 256):
             if cout % bn:
                 continue
