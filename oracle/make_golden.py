@@ -49,6 +49,12 @@ CASES: dict[str, dict] = {
                             style_w=1e9),
     "lbfgs_content_64": dict(h=64, w=64, opt="lbfgs", lr=1.0, steps=6, init="content",
                              style_w=1e10),
+    # L-BFGS (the reference's default optimiser) on a well-conditioned start: content image +
+    # noise, style and content terms of similar size.  Chosen with a TF32-emulating oracle so that
+    # TF32-level gradient differences do not fork the trajectory within 8 steps (the third step
+    # -- the first one built from a single, tiny curvature pair -- is the sensitive one).
+    "lbfgs_noisy_64": dict(h=64, w=64, opt="lbfgs", lr=1.0, steps=8, init="content",
+                           init_noise=0.3, style_w=1e8, content_w=10.0),
     # BASELINE.json configs[1] at full size (first 8 of its 300 steps; the CPU needs ~1 s per step)
     "adam_content_512_c2": dict(h=512, w=512, opt="adam", lr=0.01, steps=8, init="content"),
     # BASELINE.json configs[0]: 256x256, Adam, 50 steps, content init, on CPU
@@ -89,6 +95,9 @@ def case_inputs(cfg: dict) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor | N
     if cfg["init"] == "random":
         gen = torch.Generator().manual_seed(3)
         init = torch.randn(content.shape, generator=gen) * scale
+    elif cfg.get("init_noise"):  # content image + seeded Gaussian noise (explicit start)
+        gen = torch.Generator().manual_seed(3)
+        init = content + cfg["init_noise"] * scale * torch.randn(content.shape, generator=gen)
     return content, style, init
 
 

@@ -129,11 +129,28 @@ def launch_count() -> int:
     return _launches[0]
 
 
+_call_device: list[torch.device | None] = [None]
+
+
+def stream_for_call(device: torch.device) -> int:
+    """``stream_ptr`` for the launch being assembled; also remembers ``device`` so that ``call``
+    runs the launch with that GPU current.  The library uses the CURRENT device's context (kernel
+    attributes, SM count) and the stream must belong to it: a tensor on ``cuda:1`` must not be
+    launched on while ``cuda:0`` is current (the reference accepts ``--device cuda:1``)."""
+    _call_device[0] = device
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def call(name: str, *args) -> None:  # noqa: ANN002
     """Invoke an int-status entry point; raise with the library's message on failure."""
     lib = load()
     _launches[0] += _KERNELS_PER_CALL.get(name, 1)
-    rc = getattr(lib, name)(*args)
+    dev, _call_device[0] = _call_device[0], None
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         detail = lib.stv_last_error().decode("utf-8", "replace")
         msg = f"{name} failed (status {rc}): {detail}"

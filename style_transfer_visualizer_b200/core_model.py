@@ -9,6 +9,7 @@ fallback -- a non-sm_100 device raises.
 """
 from __future__ import annotations
 
+import weakref
 from pathlib import Path
 from urllib.parse import urlparse
 
@@ -27,7 +28,10 @@ TensorList = list[torch.Tensor]
 # ----------------------------------------------------------------------------------------------
 # torch.library custom ops.  Engines are looked up by integer handle (ops take tensors and ints).
 # ----------------------------------------------------------------------------------------------
-_ENGINES: dict[int, VggLossEngine] = {}
+# The registry holds engines WEAKLY: an engine (packed weights, side stream, multi-GB activation
+# workspaces, tensors pinned by captured graphs) lives exactly as long as the model that owns it,
+# like the reference's nn.Module state.
+_ENGINES: "weakref.WeakValueDictionary[int, VggLossEngine]" = weakref.WeakValueDictionary()
 _NEXT_HANDLE = [1]
 
 
@@ -38,17 +42,26 @@ def _register_engine(engine: VggLossEngine) -> int:
     return handle
 
 
+def _engine(handle: int) -> VggLossEngine:
+    engine = _ENGINES.get(handle)
+    if engine is None:
+        msg = ("the StyleContentModel that produced this graph has been released (or moved to "
+               "another device); run a new forward pass")
+        raise RuntimeError(msg)
+    return engine
+
+
 @torch.library.custom_op("stv_b200::vgg_losses", mutates_args=(), device_types="cuda")
 def vgg_losses(x: torch.Tensor, handle: int) -> torch.Tensor:
     """All style losses (ascending layer index) followed by all content losses, shape ``[n]``."""
-    engine = _ENGINES[handle]
+    engine = _engine(handle)
     losses, _generation = engine.forward_losses(x)
     return losses.clone()
 
 
 @vgg_losses.register_fake
 def _(x: torch.Tensor, handle: int) -> torch.Tensor:
-    engine = _ENGINES[handle]
+    engine = _engine(handle)
     return x.new_empty(len(engine.style_idx) + len(engine.content_idx))
 
 
@@ -57,7 +70,7 @@ def vgg_losses_backward(grad_losses: torch.Tensor, x: torch.Tensor, handle: int,
                         generation: int) -> torch.Tensor:
     """d(sum_k grad_losses[k] * loss_k)/dx, NCHW like ``x``.  Weights arrive on the device: the
     runner's ``style_w`` / ``content_w`` reach the kernels without a host sync."""
-    engine = _ENGINES[handle]
+    engine = _engine(handle)
     grad = engine.backward_losses(int(x.shape[2]), int(x.shape[3]), grad_losses, generation)
     return grad.clone()
 
@@ -71,7 +84,7 @@ def _setup_context(ctx, inputs, output) -> None:  # noqa: ANN001
     x, handle = inputs
     ctx.handle = handle
     # pair this forward with its activations: a later forward at the same size invalidates them
-    ctx.generation = _ENGINES[handle].generation_of(int(x.shape[2]), int(x.shape[3]))
+    ctx.generation = _engine(handle).generation_of(int(x.shape[2]), int(x.shape[3]))
     ctx.save_for_backward(x)
 
 
@@ -216,15 +229,28 @@ class StyleContentModel(nn.Module):
 
     def engine_for(self, device: torch.device) -> VggLossEngine:
         """Build (once per device) the kernel program from the current block weights."""
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         if self._engine is None or self._engine.device != device:
+            self.release()
             layers, style_idx, content_idx = self._flat_layers()
             self._engine = VggLossEngine(layers, style_idx, content_idx, device)
             self._handle = _register_engine(self._engine)
         return self._engine
 
+    def release(self) -> None:
+        """Drop the kernel program of this model (packed weights, workspaces, side stream); it is
+        rebuilt on the next use.  Called automatically when the model moves or is collected."""
+        engine, self._engine = self._engine, None
+        if engine is not None:
+            engine.release_workspaces()
+            if self._handle is not None:
+                _ENGINES.pop(self._handle, None)
+        self._handle = None
+
     def _apply(self, fn, *args, **kwargs):  # noqa: ANN001, ANN002, ANN003, ANN202
         # .to(device) / .cuda() move the nn.Module weights; the packed copies are rebuilt lazily.
-        self._engine = None
+        self.release()
         return super()._apply(fn, *args, **kwargs)
 
     # -- reference API ---------------------------------------------------------------------

@@ -367,12 +367,15 @@ int gram_launch(const float* x, long hw, int C, float* workspace, size_t workspa
   STV_REQUIRE(!loss_out || target, "gram: loss requested without a target");
   const GramPlan g = plan_gram(hw, C);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // the shared-memory opt-in is per device
+  int dev = 0;
+  STV_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  if (!attr_set[dev]) {
     STV_CHECK_CUDA(cudaFuncSetAttribute(gram_partial_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kGramSmemTotal));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   float* partials = workspace;
   float* loss_partials = workspace + static_cast<size_t>(g.splits) * g.pairs * 16384;

@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(kLbfgsThreads) lbfgs_solve_kernel(const LbfgsA
   const int lane = threadIdx.x;
 
   const float gmax = a.state_f[4], gl1 = a.state_f[5];
-  if (!(gmax > a.tol_grad)) {  // torch: opt_cond -> return before touching any state
+  if (gmax <= a.tol_grad) {  // torch: opt_cond -> return before touching any state (a NaN gradient
+                             // is NOT <= tol: like torch.optim.LBFGS the step then proceeds)
     if (lane == 0) {
       a.state_i[4] = 1;
       a.state_i[3] = 0;

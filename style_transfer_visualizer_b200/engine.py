@@ -11,6 +11,7 @@ supported; non-default positions take a few extra memory-bound passes.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass, field
 
 import torch
@@ -23,6 +24,19 @@ from . import ops
 # Default of VggLossEngine.compact_backward for engines created from now on (A/B measurements flip it
 # before building a model).
 DEFAULT_COMPACT_BACKWARD = True
+
+
+def _on_own_device(method):  # noqa: ANN001, ANN202
+    """Run an engine entry point with the engine's GPU as the current CUDA device: the native
+    launches use the current device's context (kernel attributes, SM count, stream), so a model on
+    ``cuda:1`` must not launch while ``cuda:0`` is current (reference: ``--device cuda:1``)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):  # noqa: ANN001, ANN002, ANN003, ANN202
+        if torch.cuda.current_device() == self.device.index:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
 
 
 @dataclass
@@ -68,11 +82,14 @@ class VggLossEngine:
     def __init__(self, layers: list[nn.Module], style_idx: list[int], content_idx: list[int],
                  device: torch.device) -> None:
         nat.require_device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
         self.style_idx = sorted(set(style_idx))
         self.content_idx = sorted(set(content_idx))
         self._tapped = set(self.style_idx) | set(self.content_idx)
-        self.stages = self._build_stages(layers)
+        with torch.cuda.device(device):
+            self.stages = self._build_stages(layers)
         self._workspaces: dict[tuple[int, int], _Workspace] = {}
         self.style_targets: list[torch.Tensor] | None = None          # [C, C] each
         self.content_targets_nhwc: list[torch.Tensor] | None = None   # [h, w, C] each
@@ -296,6 +313,7 @@ class VggLossEngine:
         return [i for i in (st.conv_idx, st.relu_idx, st.pool_idx)
                 if i is not None and i in self._tapped]
 
+    @_on_own_device
     def compute_targets(self, style_img: torch.Tensor, content_img: torch.Tensor) -> None:
         """reference core_model.py:192-232 -- Grams of the style image, features of the content
         image, produced by the same kernels as the per-step forward."""
@@ -330,6 +348,7 @@ class VggLossEngine:
         self.style_targets = grams
         self.content_targets_nhwc = feats
 
+    @_on_own_device
     def forward_losses(self, x: torch.Tensor) -> tuple[torch.Tensor, int]:
         """Run the stack and all losses; returns (view of the loss buffer, workspace generation).
         Loss order: style layers ascending, then content layers ascending."""
@@ -394,6 +413,7 @@ class VggLossEngine:
             accumulate = True
         return accumulate
 
+    @_on_own_device
     def backward_losses(self, height: int, width: int, grad_w: torch.Tensor,
                         generation: int | None = None) -> torch.Tensor:
         """Input gradient  sum_k grad_w[k] * d(loss_k)/dx  using the activations of the most
@@ -473,6 +493,7 @@ class VggLossEngine:
         return ws.grad_img
 
     # ------------------------------------------------------------------ introspection
+    @_on_own_device
     def tap_features_nchw(self, x: torch.Tensor) -> list[torch.Tensor]:
         """Tapped activations (ascending layer index) as NCHW copies -- for tests."""
         h, w = self._check_image(x)

@@ -20,7 +20,8 @@ def _chk(t: torch.Tensor, name: str) -> None:
 
 
 def _s(t: torch.Tensor) -> int:
-    return nat.stream_ptr(t.device)
+    """Stream argument of a launch on ``t``'s device (and makes ``nat.call`` run it there)."""
+    return nat.stream_for_call(t.device)
 
 
 def pack_conv_weights(w: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:

@@ -37,6 +37,9 @@ def case_inputs(cfg: dict) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor | N
     if cfg["init"] == "random":
         gen = torch.Generator().manual_seed(3)
         init = torch.randn(content.shape, generator=gen) * scale
+    elif cfg.get("init_noise"):  # content image + seeded Gaussian noise (explicit start)
+        gen = torch.Generator().manual_seed(3)
+        init = content + cfg["init_noise"] * scale * torch.randn(content.shape, generator=gen)
     return content, style, init
 
 

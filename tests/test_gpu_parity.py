@@ -8,19 +8,27 @@ optimisers (which call the C-ABI kernels), eagerly and through the whole-step CU
 
 Stated tolerance (TF32 multiply / FP32 accumulate in the convolutions, the Gram contraction and the
 style backward; everything else fp32) -- the reference itself runs its convolutions in TF32 on
-CUDA (torch.backends.cudnn.allow_tf32 defaults to True):
-    per-layer style loss      relative 5e-3  (measured <= 1.1e-3; stock torch on CUDA: <= 1.0e-3)
+CUDA (torch.backends.cudnn.allow_tf32 defaults to True).  The kernels are bit-reproducible, so
+every fixture has its OWN gate: 1.5 x the deviation measured on a B200 (profiles/
+r2_parity_report_v1.log), never looser than the global ceilings below.  A regression that doubles
+an error fails.
+    per-layer style loss      relative, ceiling 2e-3   (measured 1.4e-4 .. 1.2e-3)
     per-layer content loss    absolute 1e-4 x total loss   (exactly 0 for content init)
-    input gradient            relative L2 5e-2 and cosine >= 0.999  (measured <= 1.5e-2; stock
-                              torch on CUDA with cuDNN TF32 convs: <= 1.4e-2, profiles/
-                              r1_parity_vs_torch_cuda.log)
-    Adam loss trajectory      relative 3e-2 at every step
-    Adam final image          relative L2 5e-2
-    timelapse frames          <= 4 LSB, <= 20 % of bytes differing
-L-BFGS without line search amplifies 1e-2 gradient differences into different trajectories after
-two steps (it also does between torch fp32 CPU and torch TF32 CUDA); it is therefore pinned on the
-first two steps against the reference and, step by step, against torch.optim.LBFGS driven by the
-same gradients.
+    input gradient            relative L2, ceiling 3.5e-2 (measured 3.8e-3 .. 1.5e-2 up to 1080p,
+                              2.2e-2 at 3840x2160), cosine >= 0.9995.  The error is white TF32
+                              noise plus isolated ReLU-gate flips where a pre-activation rounds
+                              across zero (profiles/r2_grad_diag_1080p.log: no spatial structure)
+    Adam style-loss trajectory relative, ceiling 3e-3
+    Adam total-loss trajectory relative, ceiling 2e-2 -- except the 1080p case (9e-2): with content
+                              init the content term of step 2 is ~1e-9, created entirely by the
+                              first update, and is dominated by the gate-flip outliers
+    Adam final image          relative L2, ceiling 2e-2
+    timelapse frames          <= 3 LSB (truncating uint8 cast of values that differ by 1e-4)
+L-BFGS without line search amplifies gradient differences: its third step is built from ONE
+curvature pair whose y = g1 - g0 is a difference of nearly equal gradients.  ``lbfgs_noisy_64`` is a
+well-conditioned start chosen so that the trajectory does not fork: it is pinned for all 8 steps;
+the two older L-BFGS fixtures are pinned on their first two steps, and FusedLBFGS is pinned step by
+step against torch.optim.LBFGS driven by the same gradients.
 """
 from __future__ import annotations
 
@@ -37,11 +45,41 @@ ADAM_CASES = [n for n in cases.golden_names() if n.startswith("adam")]
 LBFGS_CASES = [n for n in cases.golden_names() if n.startswith("lbfgs")]
 
 
-def _check_first_closure(m: dict[str, float]) -> None:
-    assert m["layer_style_rel_max"] <= 5e-3
+# per-fixture gates = 1.5 x measured (profiles/r2_parity_report_v1.log), floors 3e-4 / 2e-3 (grad)
+GATES: dict[str, dict[str, float]] = {
+    "adam_clamp_64": {"layer_style_rel_max": 0.00051, "grad_rel_l2": 0.013, "total_rel_max": 0.0003, "style_rel_max": 0.0003, "final_rel_l2": 0.0001},
+    "adam_content_1080p_c3": {"layer_style_rel_max": 0.0018, "grad_rel_l2": 0.023, "total_rel_max": 0.089, "style_rel_max": 0.00063, "final_rel_l2": 0.0001, "frames_max_lsb": 1, "frames_frac_diff": 0.001},
+    "adam_content_256_c1": {"layer_style_rel_max": 0.0016, "grad_rel_l2": 0.023, "total_rel_max": 0.019, "style_rel_max": 0.0024, "final_rel_l2": 0.0025, "frames_max_lsb": 1, "frames_frac_diff": 0.13},
+    "adam_content_512_c2": {"layer_style_rel_max": 0.0014, "grad_rel_l2": 0.02, "total_rel_max": 0.019, "style_rel_max": 0.00081, "final_rel_l2": 0.00054},
+    "adam_content_64": {"layer_style_rel_max": 0.0011, "grad_rel_l2": 0.021, "total_rel_max": 0.0003, "style_rel_max": 0.00046, "final_rel_l2": 0.0014, "frames_max_lsb": 3, "frames_frac_diff": 0.024},
+    "adam_layers_024_13_64": {"layer_style_rel_max": 0.0003, "grad_rel_l2": 0.011, "total_rel_max": 0.0003, "style_rel_max": 0.0003, "final_rel_l2": 0.0013},
+    "adam_nonorm_64": {"layer_style_rel_max": 0.0017, "grad_rel_l2": 0.013, "total_rel_max": 0.004, "style_rel_max": 0.0018, "final_rel_l2": 0.00092, "frames_max_lsb": 2, "frames_frac_diff": 0.041},
+    "adam_random_4k_c5": {"layer_style_rel_max": 0.00051, "grad_rel_l2": 0.034, "total_rel_max": 0.00032, "style_rel_max": 0.00037, "final_rel_l2": 0.00017},
+    "adam_random_64": {"layer_style_rel_max": 0.00049, "grad_rel_l2": 0.022, "total_rel_max": 0.00043, "style_rel_max": 0.0003, "final_rel_l2": 0.02},
+    "adam_stylesize_96x128": {"layer_style_rel_max": 0.0014, "grad_rel_l2": 0.02, "total_rel_max": 0.00042, "style_rel_max": 0.0003, "final_rel_l2": 0.00083},
+    "adam_white_odd_70x94": {"layer_style_rel_max": 0.00047, "grad_rel_l2": 0.0058, "total_rel_max": 0.00033, "style_rel_max": 0.0003, "final_rel_l2": 0.0052},
+    "lbfgs_content_64": {"layer_style_rel_max": 0.0011, "grad_rel_l2": 0.021},
+    "lbfgs_random_64": {"layer_style_rel_max": 0.00049, "grad_rel_l2": 0.013},
+    "lbfgs_noisy_64": {"layer_style_rel_max": 0.002, "grad_rel_l2": 0.02},
+}
+LBFGS_NOISY_RTOL = 0.15    # to be tightened to 1.5 x measured
+LBFGS_NOISY_FINAL = 0.05
+CEILINGS = {"layer_style_rel_max": 2e-3, "grad_rel_l2": 3.5e-2, "total_rel_max": 2e-2,
+            "style_rel_max": 3e-3, "final_rel_l2": 2e-2, "frames_max_lsb": 3,
+            "frames_frac_diff": 0.15}
+CEILING_EXCEPTIONS = {("adam_content_1080p_c3", "total_rel_max"): 9e-2}
+
+
+def _gate(name: str, key: str) -> float:
+    ceiling = CEILING_EXCEPTIONS.get((name, key), CEILINGS[key])
+    return min(GATES.get(name, {}).get(key, ceiling), ceiling)
+
+
+def _check_first_closure(name: str, m: dict[str, float]) -> None:
+    assert m["layer_style_rel_max"] <= _gate(name, "layer_style_rel_max")
     assert m["layer_content_abs_over_total"] <= 1e-4
-    assert m["grad_rel_l2"] <= 5e-2
-    assert m["grad_cosine"] >= 0.999
+    assert m["grad_rel_l2"] <= _gate(name, "grad_rel_l2")
+    assert m["grad_cosine"] >= 0.9995
 
 
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
@@ -51,19 +89,19 @@ def test_adam_case_matches_reference(name: str, graph: bool, cuda_device, tmp_pa
     csv_path = str(tmp_path / "loss.csv") if cfg.get("csv") else None
     res = _gpu_run.run_case(cfg, cuda_device, use_cuda_graph=graph, csv_path=csv_path)
     m = _gpu_run.compare(cfg, gold, res)
-    _check_first_closure(m)
+    _check_first_closure(name, m)
     assert len(res.total) == cfg["steps"]
-    assert m["total_rel_max"] <= 3e-2
-    assert m["style_rel_max"] <= 3e-2
-    assert m["final_rel_l2"] <= 5e-2
+    assert m["total_rel_max"] <= _gate(name, "total_rel_max")
+    assert m["style_rel_max"] <= _gate(name, "style_rel_max")
+    assert m["final_rel_l2"] <= _gate(name, "final_rel_l2")
     if cfg["init"] == "content":
         assert res.content[0] == 0.0  # targets come from the same kernels as the step forward
     if "frames_max_lsb" in m:
         assert len(res.frames) == cfg["steps"] // cfg["save_every"]
         assert res.frames[0].dtype == np.uint8
         assert res.frames[0].shape == (cfg["h"], cfg["w"], 3)
-        assert m["frames_max_lsb"] <= 4
-        assert m["frames_frac_diff"] <= 0.2
+        assert m["frames_max_lsb"] <= _gate(name, "frames_max_lsb")
+        assert m["frames_frac_diff"] <= _gate(name, "frames_frac_diff")
     if csv_path:
         lines = res.csv_text.strip().splitlines()
         assert lines[0] == "step,style_loss,content_loss,total_loss"
@@ -75,9 +113,18 @@ def test_adam_case_matches_reference(name: str, graph: bool, cuda_device, tmp_pa
 def test_lbfgs_first_steps_match_reference(name: str, cuda_device) -> None:  # noqa: ANN001
     cfg, gold = cases.load_golden(name)
     res = _gpu_run.run_case(cfg, cuda_device, use_cuda_graph=False)
-    _check_first_closure(_gpu_run.compare(cfg, gold, res))
-    np.testing.assert_allclose(res.total[:2], gold["total_loss"][:2], rtol=1e-2)
+    m = _gpu_run.compare(cfg, gold, res)
+    _check_first_closure(name, m)
+    np.testing.assert_allclose(res.total[:2], gold["total_loss"][:2], rtol=2e-3)
     assert res.total[-1] < res.total[0]  # it optimises
+    if name == "lbfgs_noisy_64":
+        # the reference's DEFAULT optimiser pinned over the whole 8-step run, eagerly and through
+        # the device-resident graph-captured step
+        assert len(res.total) == 8
+        np.testing.assert_allclose(res.total, gold["total_loss"], rtol=LBFGS_NOISY_RTOL)
+        assert m["final_rel_l2"] <= LBFGS_NOISY_FINAL
+        res_g = _gpu_run.run_case(cfg, cuda_device, use_cuda_graph=True)
+        np.testing.assert_allclose(res_g.total, gold["total_loss"], rtol=LBFGS_NOISY_RTOL)
 
 
 def test_fused_lbfgs_tracks_torch_lbfgs(cuda_device) -> None:  # noqa: ANN001
@@ -382,3 +429,89 @@ def test_image_load_kernel_is_bit_identical_to_torchvision(cuda_device, tmp_path
             want = transforms.Compose(pipeline)(Image.open(path).convert("RGB")).unsqueeze(0)
             assert got.device.type == "cuda" and got.shape == want.shape
             assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+def test_non_finite_warnings_are_deferred_to_the_log_cadence(graph: bool, cuda_device) -> None:  # noqa: ANN001, FBT001
+    """Reference optimization.py:375-400: one warning per non-finite score per step.  On CUDA the
+    flags are produced on the device (``stv_step_scores`` inside the captured graph, or
+    ``stv_finite_flags`` for eager steps) and read back only when the host syncs for logging, in
+    step order, with the reference's message texts -- no per-closure host sync."""
+    import logging
+
+    from style_transfer_visualizer_b200.config import StyleTransferConfig
+    from style_transfer_visualizer_b200.logging_utils import logger
+    from style_transfer_visualizer_b200.optim import FusedAdam
+    from style_transfer_visualizer_b200.optimization import (OptimizationCallbacks,
+                                                             OptimizationRunner)
+
+    cfg, _gold = cases.load_golden("adam_content_64")
+    model, x0 = _gpu_run.build_model(cfg, cuda_device)
+    # poison one style target: style score and total become NaN at step 1; the NaN gradient then
+    # makes the image (hence the content score) NaN from step 2 on
+    model.engine_for(cuda_device).style_targets[1][0, 0] = float("nan")
+    x = x0.clone().requires_grad_(True)
+    config = StyleTransferConfig.model_validate({
+        "optimization": {"steps": 6, "style_w": 1e5, "content_w": 1.0, "lr": 0.01},
+        "video": {"save_every": 7}, "output": {"log_every": 3}})
+
+    records: list[str] = []
+
+    class Grab(logging.Handler):
+        def emit(self, record: logging.LogRecord) -> None:
+            if record.levelno >= logging.WARNING:
+                records.append(record.getMessage())
+
+    seen_at_step: list[int] = []
+    handler = Grab()
+    logger.addHandler(handler)
+    try:
+        runner = OptimizationRunner(
+            model, x, config, optimizer=FusedAdam([x], lr=0.01), progress_bar=_gpu_run.NullBar(),
+            callbacks=OptimizationCallbacks(on_step_end=lambda m: seen_at_step.append(len(records))),
+            use_cuda_graph=graph)
+        runner.run()
+    finally:
+        logger.removeHandler(handler)
+    want = []
+    for step in range(1, 7):
+        want.append(f"Non-finite style score at step {step}")
+        if step >= 2:
+            want.append(f"Non-finite content score at step {step}")
+        want.append(f"Non-finite total loss at step {step}, using previous loss")
+    assert records == want
+    # nothing is emitted between logging syncs: steps 1-2 see no warning yet, step 3 flushes 1..3
+    assert seen_at_step[:2] == [0, 0]
+    assert seen_at_step[2] == 2 + 3 + 3
+    assert seen_at_step[3] == seen_at_step[4] == seen_at_step[2]
+    assert seen_at_step[5] == len(want)
+
+
+def test_models_release_their_gpu_memory(cuda_device) -> None:  # noqa: ANN001
+    """An engine (packed weights, activation / gradient workspaces) lives exactly as long as the
+    model that owns it: creating and dropping models must not grow the allocated GPU memory (the
+    engine registry used by the custom ops holds weak references only)."""
+    import gc
+
+    import style_transfer_visualizer_b200.core_model as cm
+
+    cfg, _gold = cases.load_golden("adam_content_64")
+
+    def one_model() -> None:
+        model, x0 = _gpu_run.build_model(cfg, cuda_device)
+        x = x0.clone().requires_grad_(True)
+        sl, cl = model(x)
+        (1e5 * torch.stack(sl).sum() + torch.stack(cl).sum()).backward()
+        assert model.engine_for(cuda_device).workspace_bytes(cfg["h"], cfg["w"]) > 0
+
+    one_model()  # one-off allocations (cuBLAS-free path, but torch caches a few small buffers)
+    gc.collect()
+    torch.cuda.synchronize(cuda_device)
+    base = torch.cuda.memory_allocated(cuda_device)
+    registered = len(cm._ENGINES)  # noqa: SLF001
+    for _ in range(3):
+        one_model()
+    gc.collect()
+    torch.cuda.synchronize(cuda_device)
+    assert len(cm._ENGINES) <= registered  # noqa: SLF001
+    assert torch.cuda.memory_allocated(cuda_device) <= base + (1 << 20)
