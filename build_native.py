@@ -9,7 +9,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "style_transfer_visualizer_b200" / "csrc"
 OUT = ROOT / "style_transfer_visualizer_b200" / "lib" / "libstv_b200.so"
 SOURCES = ["api.cu", "conv_igemm2.cu", "gram.cu", "conv_direct.cu", "elementwise.cu",
-           "lbfgs.cu"]
+           "lbfgs.cu", "halo.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

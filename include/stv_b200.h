@@ -206,6 +206,19 @@ int stv_step_scores(const float* losses, int n_style, int n_content, float style
                     float* scores3, float* loss_ring, int* finite_ring, int capacity, int* counter,
                     void* stream);
 
+/* ---- row-band sharding over several GPUs (BASELINE configs[4]; no reference counterpart) ----- */
+/* Halo exchange of one haloed buffer [rows + 2][row_floats] (x planes) through PEER-MAPPED memory:
+ * this GPU's kernels store its first / last own row into the lower halo of the rank above (`up`,
+ * which has rows_up own rows) and the upper halo of the rank below (`down`), zero its own halo at
+ * the image boundary (NULL neighbour), and hand-shake through flag words.  `up` / `down` /
+ * `flags_up` / `flags_down` are this process's mappings of the NEIGHBOURS' buffers (symmetric
+ * memory); flags_*: [slots][4] words, zero-initialised; epoch / done: local [slots] words,
+ * zero-initialised.  Every rank must issue the same sequence of (slot) exchanges.  On completion (in
+ * stream order) the two halo rows of `mine` hold the neighbours' rows.  Graph-capturable. */
+int stv_halo_exchange(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
+                      long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
+                      unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, void* stream);
+
 /* ---- test hooks ---------------------------------------------------------------------------- */
 /* Explicit tile selection for the tensor-core conv: out = alpha*conv(x,w)+bias, optional relu gate /
  * accumulate, as in stv_conv3x3_fwd / _dgrad.  taps = 9 or 1; block_n in {64,128,256}, m_halves in

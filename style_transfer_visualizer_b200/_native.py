@@ -63,6 +63,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_nchw_to_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "stv_nhwc_to_nchw": [_vp, _i, _i, _i, _vp, _vp],
     "stv_finite_flags": [_vp, _i, _vp, _vp],
+    "stv_halo_exchange": [_vp, _vp, _vp, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "stv_step_scores": [_vp, _i, _i, _f, _f, _vp, _vp, _vp, _i, _vp, _vp],
     "stv_conv_igemm2_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                            _vp],
@@ -119,7 +120,7 @@ def stream_ptr(device: torch.device | None = None) -> int:
 
 # kernels enqueued per entry point (everything else launches exactly one)
 _KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_gram_partial_r": 2, "stv_gram_from_r": 2, "stv_content_loss_fwd": 2, "stv_dot": 2,
-                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0,
+                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_halo_exchange": 2, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0,
                      "stv_device_check": 0}
 _launches = [0]
 

@@ -328,6 +328,13 @@ int stv_step_scores(const float* losses, int n_style, int n_content, float style
                             finite_ring, capacity, counter, S(stream));
 }
 
+int stv_halo_exchange(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
+                      long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
+                      unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, void* stream) {
+  return halo_exchange_launch(mine, up, down, rows, rows_up, rows_down, row_floats, planes,
+                              flags_mine, flags_up, flags_down, epoch, done, slot, S(stream));
+}
+
 int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,
                        const float* bias, const float* alpha, const float* mask_src,
                        const float* add_src, float* out_pre, float* out_post, int block_n,

@@ -101,8 +101,8 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
         if (out_post || out_bits) {
           float4 r;
           // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
-          r.x = round_tf32(fmaxf(acc[px].x, 0.f)); r.y = round_tf32(fmaxf(acc[px].y, 0.f));
-          r.z = round_tf32(fmaxf(acc[px].z, 0.f)); r.w = round_tf32(fmaxf(acc[px].w, 0.f));
+          r.x = round_tf32(relu_nan(acc[px].x)); r.y = round_tf32(relu_nan(acc[px].y));
+          r.z = round_tf32(relu_nan(acc[px].z)); r.w = round_tf32(relu_nan(acc[px].w));
           if (out_post) reinterpret_cast<float4*>(out_post)[o] = r;
           const uint32_t nib = (r.x > 0.f ? 1u : 0u) | (r.y > 0.f ? 2u : 0u) |
                                (r.z > 0.f ? 4u : 0u) | (r.w > 0.f ? 8u : 0u);

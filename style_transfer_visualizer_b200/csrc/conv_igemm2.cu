@@ -477,8 +477,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   }
                   if (want_post) {
                     float4 o;
-                    o.x = fmaxf(v.x, 0.f); o.y = fmaxf(v.y, 0.f);
-                    o.z = fmaxf(v.z, 0.f); o.w = fmaxf(v.w, 0.f);
+                    o.x = relu_nan(v.x); o.y = relu_nan(v.y);
+                    o.z = relu_nan(v.z); o.w = relu_nan(v.w);
                     if (p.round_post) {
                       o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                       o.z = round_tf32(o.z); o.w = round_tf32(o.w);
@@ -498,7 +498,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                         const float nb = __shfl_xor_sync(0xffffffffu, ov[e], 1);
                         const float a = odd_x ? nb : ov[e];
                         const float bb = odd_x ? ov[e] : nb;
-                        const bool k0 = bb > a;
+                        const bool k0 = (bb > a) || (bb != bb);  // ATen: (val > max) || isnan(val)
                         m0[e] = k0 ? bb : a;
                         kb |= (k0 ? 1u : 0u) << e;
                       }
@@ -509,7 +509,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
                       for (int e = 0; e < 4; ++e) {
                         const float mo = __shfl_xor_sync(0xffffffffu, m0[e], p.tw);
-                        const bool lower = mo > m0[e];
+                        const bool lower = (mo > m0[e]) || (mo != mo);
                         mx[e] = lower ? mo : m0[e];
                         const uint32_t k = lower ? (2u | ((kbo >> e) & 1u)) : ((kb >> e) & 1u);
                         c16 |= (k | (mx[e] > 0.f ? 4u : 0u)) << (4 * e);
@@ -617,8 +617,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 }
                 if (p.out_post) {
                   float4 o;
-                  o.x = fmaxf(v.x, 0.f); o.y = fmaxf(v.y, 0.f);
-                  o.z = fmaxf(v.z, 0.f); o.w = fmaxf(v.w, 0.f);
+                  o.x = relu_nan(v.x); o.y = relu_nan(v.y);
+                  o.z = relu_nan(v.z); o.w = relu_nan(v.w);
                   if (p.round_post) {
                     o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                     o.z = round_tf32(o.z); o.w = round_tf32(o.w);

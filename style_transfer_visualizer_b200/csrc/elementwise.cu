@@ -136,7 +136,7 @@ __global__ void relu_fwd_kernel(const float4* __restrict__ x, long n4, float4* _
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(x + i);
-    y[i] = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    y[i] = make_float4(relu_nan(v.x), relu_nan(v.y), relu_nan(v.z), relu_nan(v.w));
   }
 }
 __global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,

@@ -370,6 +370,14 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// ReLU with torch's NaN behaviour: relu(NaN) = NaN (fmaxf would return 0 and hide a diverged run
+// from the reference's non-finite checks, optimization.py:375-391).
+__device__ __forceinline__ float relu_nan(float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

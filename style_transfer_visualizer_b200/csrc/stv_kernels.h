@@ -97,4 +97,10 @@ int step_scores_launch(const float* losses, int n_style, int n_content, float st
                        float content_w, float* scores3, float* loss_ring, int* finite_ring,
                        int capacity, int* counter, cudaStream_t stream);
 
+// halo.cu: row-band sharding, halo rows pushed into the neighbours' buffers over NVLink
+int halo_exchange_launch(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
+                         long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
+                         unsigned* flags_down, unsigned* epoch, unsigned* done, int slot,
+                         cudaStream_t stream);
+
 }  // namespace stv

@@ -6,8 +6,12 @@ never straddle a band boundary.  Per step:
 
   * every activation / gradient buffer carries one halo row above and below its band;
   * a 3x3 conv (or dgrad) is run over the band *including* its halo rows, which makes the band's own
-    rows exact; the two halo rows of the result are then refreshed from the neighbours with one
-    NCCL send/recv pair per direction (image-boundary halos are zeroed = the conv's zero padding);
+    rows exact; the two halo rows of the result are then refreshed from the neighbours: every rank's
+    own kernel stores its boundary rows straight into the neighbours' halo rows over NVLink
+    (activation buffers live in peer-mapped symmetric memory, ``stv_halo_exchange``; flag words
+    hand-shake, no NCCL call on the path).  Where symmetric memory is unavailable the exchange
+    falls back to one NCCL send/recv pair per direction (image-boundary halos are zeroed = the
+    conv's zero padding);
   * each rank contracts its own pixels into a raw Gram partial; ONE all-reduce per step sums the five
     C x C partials (and the content-loss partial sums) over NVLink, after which clamp / 1/N / MSE /
     backward seed are applied to the global matrices on every rank (the clamp is non-linear, so it
@@ -69,6 +73,48 @@ def exchange_rows(buf: torch.Tensor, rank: int, world_size: int, group=None) -> 
             req.wait()
 
 
+def rows_at(band: int, level: int) -> int:
+    """Own rows of a band after ``level`` floor-mode 2x2 pools."""
+    for _ in range(level):
+        band //= 2
+    return band
+
+
+class _PeerArena:
+    """Symmetric (peer-mapped) memory of one workspace: ONE arena holding every haloed buffer, so a
+    single rendezvous maps all of them into the neighbours' address spaces, plus the flag words of
+    the halo hand-shake.  All ranks allocate identical sizes (sized for the largest band)."""
+
+    MAX_SLOTS = 64
+
+    def __init__(self, total_floats: int, device: torch.device, group) -> None:  # noqa: ANN001
+        import torch.distributed._symmetric_memory as symm
+
+        grp = group if group is not None else dist.group.WORLD
+        self.arena = symm.empty(total_floats, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.arena, grp)
+        self.flags = symm.empty(self.MAX_SLOTS * 4, dtype=torch.int32, device=device)
+        self.flag_handle = symm.rendezvous(self.flags, grp)
+        self.arena.zero_()
+        self.flags.zero_()
+        self.epoch = torch.zeros(self.MAX_SLOTS, device=device, dtype=torch.int32)
+        self.done = torch.zeros(self.MAX_SLOTS, device=device, dtype=torch.int32)
+        self.base = [int(p) for p in self.handle.buffer_ptrs]
+        self.flag_base = [int(p) for p in self.flag_handle.buffer_ptrs]
+        self.used = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)   # nobody pushes into an arena that is still being zeroed
+
+    def take(self, n_floats: int) -> tuple[torch.Tensor, int]:
+        """Next ``n_floats`` of the arena (256-byte aligned): (flat view, offset in floats)."""
+        off = self.used
+        self.used += (n_floats + 63) // 64 * 64
+        if self.used > self.arena.numel():
+            msg = "symmetric arena exhausted (sizing bug)"
+            raise RuntimeError(msg)
+        return self.arena[off:off + n_floats], off
+
+
 @dataclass
 class _BandWorkspace:
     band: int                       # own rows at full resolution
@@ -89,6 +135,11 @@ class _BandWorkspace:
     grad_h: torch.Tensor | None = None                  # [1, 3, band + 2, W]
     img_send: torch.Tensor | None = None
     img_recv: torch.Tensor | None = None
+    bands: list[tuple[int, int]] = field(default_factory=list)   # band plan of the whole image
+    peer: _PeerArena | None = None                      # NVLink halo exchange (else NCCL)
+    peer_g: _PeerArena | None = None                    # same for the gradient buffers
+    # data_ptr of a haloed buffer -> (arena offset in floats, pooling level of its rows)
+    where: dict[int, tuple[int, int]] = field(default_factory=dict)
 
 
 class RowBandEngine:
@@ -112,17 +163,53 @@ class RowBandEngine:
             msg = "row-band sharding supports losses on convolution outputs only (the default taps)"
             raise NotImplementedError(msg)
         self._ws: dict[tuple[int, int], _BandWorkspace] = {}
+        # "nvlink-peer": boundary rows stored into the neighbours' buffers by this GPU's kernels;
+        # "nccl": send/recv pairs.  STV_HALO=nccl forces the fallback (A/B measurements).
+        import os
+
+        self.halo_mode = "nccl" if os.environ.get("STV_HALO") == "nccl" or self.world == 1 \
+            else "nvlink-peer"
+        self.bands: list[tuple[int, int]] | None = None   # set per image (plan_bands)
         self.style_targets: list[torch.Tensor] | None = None
         self.content_targets: list[torch.Tensor] | None = None   # own rows, NHWC
         self.full_hw: tuple[int, int] | None = None
         self.band_rows: tuple[int, int] | None = None
 
     # ------------------------------------------------------------------ helpers
-    def _xchg(self, buf: torch.Tensor) -> None:
-        exchange_rows(buf, self.rank, self.world, self.group)
+    def _xchg(self, ws: _BandWorkspace, buf: torch.Tensor, slot: int, planes: int = 1, *,
+              grads: bool = False) -> None:
+        """Refresh the halo rows of ``buf`` from the neighbouring ranks (zeros at the image edge)."""
+        pa = ws.peer_g if grads else ws.peer
+        if pa is None or (buf.shape[-1] * (1 if planes == 3 else buf.shape[-2])) % 4:
+            if planes == 3:   # NCHW image band: packed rows through NCCL
+                self._xchg_image_nccl(ws, buf)
+            else:
+                exchange_rows(buf, self.rank, self.world, self.group)
+            return
+        off, level = ws.where[buf.data_ptr()]
+        band_of = [y1 - y0 for (y0, y1) in ws.bands]
+        rows = rows_at(band_of[self.rank], level)
+        up = self.rank - 1 if self.rank > 0 else None
+        down = self.rank + 1 if self.rank < self.world - 1 else None
+        row_floats = buf.numel() // ((rows + 2) * planes)
+        ops.halo_exchange(
+            buf, up_ptr=None if up is None else pa.base[up] + 4 * off,
+            down_ptr=None if down is None else pa.base[down] + 4 * off,
+            rows=rows, rows_up=0 if up is None else rows_at(band_of[up], level),
+            rows_down=0 if down is None else rows_at(band_of[down], level),
+            row_floats=row_floats, planes=planes, flags_mine=pa.flags,
+            flags_up_ptr=None if up is None else pa.flag_base[up],
+            flags_down_ptr=None if down is None else pa.flag_base[down],
+            epoch=pa.epoch, done=pa.done, slot=slot)
 
     def _xchg_image(self, ws: _BandWorkspace, img_h: torch.Tensor) -> None:
         """Halo rows of the NCHW image band: the 3 planes' rows are packed into one message."""
+        if ws.peer is not None and img_h is ws.x_h:
+            self._xchg(ws, img_h, slot=0, planes=3)
+            return
+        self._xchg_image_nccl(ws, img_h)
+
+    def _xchg_image_nccl(self, ws: _BandWorkspace, img_h: torch.Tensor) -> None:
         b = ws.band
         send, recv = ws.img_send, ws.img_recv
         send[0].copy_(img_h[0, :, 1, :])
@@ -147,6 +234,8 @@ class RowBandEngine:
             img_h[0, :, b + 1, :].zero_()
 
     def _workspace(self, band: int, width: int, *, with_grad: bool) -> _BandWorkspace:
+        """Buffers of one (band, width); creating one is COLLECTIVE in nvlink-peer mode (symmetric
+        allocation + rendezvous), and every rank creates its workspaces in the same order."""
         key = (band, width)
         ws = self._ws.get(key)
         dev = self.device
@@ -154,23 +243,80 @@ class RowBandEngine:
         def buf(*shape: int) -> torch.Tensor:
             return torch.zeros(*shape, device=dev, dtype=torch.float32)
 
+        def haloed_specs(grads: bool) -> list[tuple[str, int, int, int, int, int]]:
+            """(list name, stage, pooling level, cols, channels, planes) of every haloed buffer."""
+            out = []
+            level, cols = 0, width
+            if not grads:
+                out.append(("x_h", -1, 0, width, 1, 3))
+            for s, st in enumerate(self.stages):
+                tapped = st.conv_idx in self.style_idx or st.conv_idx in self.content_idx
+                if grads:
+                    out.append(("d_y", s, level, cols, st.cout, 1))
+                else:
+                    if tapped or st.relu_idx is None:
+                        out.append(("pre", s, level, cols, st.cout, 1))
+                    if st.relu_idx is not None:
+                        out.append(("post", s, level, cols, st.cout, 1))
+                if st.pool_idx is not None:
+                    level, cols = level + 1, cols // 2
+                    out.append(("d_pool" if grads else "pool", s, level, cols, st.cout, 1))
+            return out
+
+        def allocate(specs, arena: _PeerArena | None) -> None:  # noqa: ANN001
+            for name, s, level, cols, ch, planes in specs:
+                rows = rows_at(band, level)
+                shape = (1, 3, rows + 2, cols) if planes == 3 else (rows + 2, cols, ch)
+                if arena is None:
+                    t = buf(*shape)
+                else:
+                    rmax = rows_at(max(y1 - y0 for (y0, y1) in ws.bands), level)
+                    flat, off = arena.take(planes * (rmax + 2) * cols * ch)
+                    n = planes * (rows + 2) * cols * ch
+                    t = flat[:n].view(shape)
+                    ws.where[t.data_ptr()] = (off, level)
+                if name == "x_h":
+                    ws.x_h = t
+                else:
+                    getattr(ws, name)[s] = t
+
+        def arena_for(specs) -> _PeerArena | None:  # noqa: ANN001
+            if self.halo_mode != "nvlink-peer":
+                return None
+            bmax = max(y1 - y0 for (y0, y1) in ws.bands)
+            total = sum((planes * (rows_at(bmax, level) + 2) * cols * ch + 63) // 64 * 64
+                        for _n, _s, level, cols, ch, planes in specs)
+            try:
+                return _PeerArena(total, dev, self.group)
+            except Exception as exc:  # noqa: BLE001
+                # plumbing fallback (all ranks fail or succeed together: same driver, same node)
+                from .logging_utils import logger
+
+                logger.warning("symmetric memory unavailable (%s: %s); halo exchange falls back "
+                               "to NCCL send/recv", type(exc).__name__, exc)
+                self.halo_mode = "nccl"
+                return None
+
         if ws is None:
             ws = _BandWorkspace(band=band, width=width)
+            full_h = self.full_hw[0] if self.full_hw is not None else band * self.world
+            ws.bands = plan_bands(full_h, self.world)
+            if ws.bands[self.rank][1] - ws.bands[self.rank][0] != band:
+                msg = (f"band of {band} rows does not match the band plan of a {full_h}-row image "
+                       f"for rank {self.rank}: {ws.bands}")
+                raise ValueError(msg)
+            n = len(self.stages)
             rows, cols = band, width
             for st in self.stages:
                 ws.rows.append(rows)
                 ws.cols.append(cols)
-                tapped = st.conv_idx in self.style_idx or st.conv_idx in self.content_idx
-                ws.pre.append(buf(rows + 2, cols, st.cout) if tapped or st.relu_idx is None
-                              else None)
-                ws.post.append(buf(rows + 2, cols, st.cout) if st.relu_idx is not None else None)
                 if st.pool_idx is not None:
                     rows, cols = rows // 2, cols // 2
-                    ws.pool.append(buf(rows + 2, cols, st.cout))
-                else:
-                    ws.pool.append(None)
-                ws.d_y.append(None)
-                ws.d_pool.append(None)
+            for name in ("pre", "post", "pool", "d_y", "d_pool"):
+                setattr(ws, name, [None] * n)
+            specs = haloed_specs(grads=False)
+            ws.peer = arena_for(specs)
+            allocate(specs, ws.peer)
             total = 0
             for idx in self.style_idx:
                 s = self._stage(idx)
@@ -181,15 +327,13 @@ class RowBandEngine:
             ws.reduce_buf = buf(total + len(self.content_idx))
             ws.losses = buf(len(self.style_idx) + len(self.content_idx))
             ws.scratch = buf(2 * nat.reduce_scratch_floats() + 1024)
-            ws.x_h = buf(1, 3, band + 2, width)
             ws.img_send = buf(2, 3, width)
             ws.img_recv = buf(2, 3, width)
             self._ws[key] = ws
         if with_grad and ws.grad_h is None:
-            for s, st in enumerate(self.stages):
-                ws.d_y[s] = buf(ws.rows[s] + 2, ws.cols[s], st.cout)
-                if st.pool_idx is not None:
-                    ws.d_pool[s] = buf(ws.rows[s] // 2 + 2, ws.cols[s] // 2, st.cout)
+            specs = haloed_specs(grads=True)
+            ws.peer_g = arena_for(specs) if ws.peer is not None else None
+            allocate(specs, ws.peer_g)
             ws.grad_h = buf(1, 3, band + 2, width)
         return ws
 
@@ -233,7 +377,7 @@ class RowBandEngine:
                 ops.maxpool2_fwd(self._own(ws.post[s]), self._own(ws.pool[s]))
                 cur = ws.pool[s]
             if s + 1 < n:
-                self._xchg(cur)  # halos for the next 3x3 conv
+                self._xchg(ws, cur, slot=1 + s)  # halos for the next 3x3 conv
 
     def _reduce_grams(self, ws: _BandWorkspace, content_sums: list[torch.Tensor]) -> list[torch.Tensor]:
         """Raw Gram partials of the tapped layers + content partial sums -> ONE all-reduce."""
@@ -343,7 +487,7 @@ class RowBandEngine:
                                   accumulate=acc)
             else:
                 tap_grads(False)
-            self._xchg(d_y)  # halos of the finished gradient feed the next dgrad
+            self._xchg(ws, d_y, slot=s, grads=True)  # halos of the finished gradient feed the next dgrad
         ops.conv3x3_first_dgrad_tc(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_h)
         return ws.grad_h[:, :, 1:-1, :]
 

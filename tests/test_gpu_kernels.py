@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", ["elementwise", "conv", "conv2", "conv_variants", "conv_compact", "gram"])
+@pytest.mark.parametrize("case", ["elementwise", "conv", "conv2", "conv_variants", "conv_compact", "halo", "gram"])
 def test_kernel_case(case: str) -> None:
     proc = subprocess.run([sys.executable, str(ROOT / "tools" / "gpu_selftest.py"), "--case", case],
                           capture_output=True, text=True, timeout=600, check=False, cwd=ROOT)

@@ -1,6 +1,7 @@
 """Row-band sharding on real GPUs (needs >= 2 B200s; skipped on a single-GPU box): the sharded
 model must reproduce the single-GPU losses / gradient / Adam trajectory (tools/sharded_check.py,
-launched as one process per GPU over NCCL)."""
+launched as one process per GPU over NCCL), and the sharded 3840x2160 first closure must match the
+REFERENCE's golden fixture (tests/golden/adam_random_4k_c5.npz)."""
 from __future__ import annotations
 
 import subprocess
@@ -23,7 +24,7 @@ def test_row_band_sharding_matches_single_gpu() -> None:
     proc = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
          "--master-addr", "127.0.0.1", "--master-port", "29547",
-         str(ROOT / "tools" / "sharded_check.py")],
+         str(ROOT / "tools" / "sharded_check.py"), "--golden4k"],
         capture_output=True, text=True, timeout=900, check=False, cwd=ROOT)
     lines = [ln for ln in proc.stdout.splitlines() if ln.startswith(("PASS", "FAIL"))]
     assert proc.returncode == 0 and lines and all(ln.startswith("PASS") for ln in lines), \

@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-CASES = ["elementwise", "conv", "conv2", "conv_variants", "conv_compact", "gram", "perf"]
+CASES = ["elementwise", "conv", "conv2", "conv_variants", "conv_compact", "halo", "gram", "perf"]
 
 
 def rel_l2(a, b):  # noqa: ANN001, ANN201
@@ -522,6 +522,51 @@ def case_conv_compact() -> bool:
                          0.0 if torch.equal(got, want) else 1.0, 0.0)
         ops.conv_set_tuning()
     torch.cuda.synchronize()
+    return ok
+
+
+def case_halo() -> bool:
+    """stv_halo_exchange with three "ranks" emulated on ONE GPU: each rank is a stream, the
+    neighbours' peer pointers are ordinary device pointers of the same process.  The three exchange
+    launches are co-resident and hand-shake through the flag words exactly as across GPUs."""
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    dev = torch.device("cuda")
+    ok = True
+    for planes, rows_of, cols, ch in [(1, (8, 8, 6), 20, 64), (1, (5, 7, 3), 12, 128),
+                                      (3, (16, 16, 12), 64, 1), (1, (4, 4, 4), 960, 64)]:
+        n = len(rows_of)
+        row_floats = cols * ch
+        bufs = [torch.zeros(planes, rows + 2, row_floats, device=dev) for rows in rows_of]
+        flags = [torch.zeros(64 * 4, device=dev, dtype=torch.int32) for _ in range(n)]
+        epoch = [torch.zeros(64, device=dev, dtype=torch.int32) for _ in range(n)]
+        done = [torch.zeros(64, device=dev, dtype=torch.int32) for _ in range(n)]
+        streams = [torch.cuda.Stream() for _ in range(n)]
+        for it in range(3):
+            for r in range(n):
+                bufs[r].copy_(torch.randn(bufs[r].shape, device=dev))   # halos hold junk
+            want = [b.clone() for b in bufs]
+            for r in range(n):
+                want[r][:, 0] = want[r - 1][:, rows_of[r - 1]] if r > 0 else 0.0
+                want[r][:, rows_of[r] + 1] = bufs[r + 1][:, 1] if r < n - 1 else 0.0
+            torch.cuda.synchronize()
+            for r in range(n):
+                with torch.cuda.stream(streams[r]):
+                    ops.halo_exchange(
+                        bufs[r], up_ptr=bufs[r - 1].data_ptr() if r > 0 else None,
+                        down_ptr=bufs[r + 1].data_ptr() if r < n - 1 else None,
+                        rows=rows_of[r], rows_up=rows_of[r - 1] if r > 0 else 0,
+                        rows_down=rows_of[r + 1] if r < n - 1 else 0, row_floats=row_floats,
+                        planes=planes, flags_mine=flags[r],
+                        flags_up_ptr=flags[r - 1].data_ptr() if r > 0 else None,
+                        flags_down_ptr=flags[r + 1].data_ptr() if r < n - 1 else None,
+                        epoch=epoch[r], done=done[r], slot=5)
+            torch.cuda.synchronize()
+            same = all(torch.equal(bufs[r], want[r]) for r in range(n))
+            ok &= report(f"halo exchange planes={planes} rows={rows_of} row={row_floats} it={it}",
+                         0.0 if same else 1.0, 0.0)
     return ok
 
 

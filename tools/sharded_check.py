@@ -24,6 +24,40 @@ def rel(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
 
 
+def golden_4k(info, dev) -> bool:  # noqa: ANN001
+    """The SHARDED first closure at 3840x2160 against tests/golden/adam_random_4k_c5.npz -- outputs
+    of the unmodified reference on the CPU (oracle/make_golden.py), not of this package's
+    single-GPU path.  Gates = 1.5 x the single-GPU deviation from the same fixture."""
+    import numpy as np
+
+    gold = np.load(ROOT / "tests" / "golden" / "adam_random_4k_c5.npz", allow_pickle=False)
+    h, w = 2160, 3840
+    feats = synthetic.random_vgg19_features(0)
+    content = synthetic.synthetic_image(1, h, w)
+    style = synthetic.synthetic_image(2, h, w)
+    start = torch.randn(content.shape, generator=torch.Generator().manual_seed(3))
+    model = ShardedStyleContentModel(feats, [0, 5, 10, 19, 28], [21], dev)
+    model.set_targets(style, content)
+    x = model.band_of(start).requires_grad_(True)
+    sl, cl = model(x)
+    (1e5 * torch.stack(sl).sum() + torch.stack(cl).sum()).backward()
+    full = model.gather_image(x.grad)
+    if info.rank != 0:
+        return True
+    g = full.detach().cpu().numpy()[..., ::8, ::8].astype(np.float64)
+    ref = gold["first_grad"].astype(np.float64)
+    e_grad = float(np.linalg.norm(g - ref) / np.linalg.norm(ref))
+    ls = np.array([float(v.detach()) for v in sl])
+    lc = np.array([float(v.detach()) for v in cl])
+    e_style = float(np.max(np.abs(ls - gold["layer_style"]) / gold["layer_style"]))
+    e_content = float(np.max(np.abs(lc - gold["layer_content"]) / gold["layer_content"]))
+    good = e_grad <= 0.034 and e_style <= 5.1e-4 and e_content <= 1e-3
+    print(f"{'PASS' if good else 'FAIL'} sharded x{info.world_size} 3840x2160 vs reference golden "
+          f"(halo: {model.engine.halo_mode}): grad_rel_l2={e_grad:.3e} layer_style_rel_max="
+          f"{e_style:.3e} content_rel={e_content:.3e}", flush=True)
+    return good
+
+
 def main() -> int:
     info = jobs.init_distributed()
     dev = torch.device("cuda", info.local_rank)
@@ -105,6 +139,8 @@ def main() -> int:
                   f"bands={plan_bands(h, info.world_size)} loss_rel={e_loss:.2e} grad_rel={e_grad:.2e} "
                   f"adam_loss_rel={e_hist:.2e} final_rel={e_final:.2e} step={dt * 1e3:.2f} ms",
                   flush=True)
+    if "--golden4k" in sys.argv:
+        ok &= golden_4k(info, dev)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     jobs.barrier()
