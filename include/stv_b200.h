@@ -72,12 +72,12 @@ int stv_conv3x3_fwd_bits(const float* x, const float* w_fwd, const float* bias, 
 int stv_conv3x3_fwd_pool(const float* x, const float* w_fwd, const float* bias, int H, int W,
                          int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
                          int round_pre, void* stream);
-/* Same, also recording what autograd's max_pool2d + ReLU backward need: out_code
- * [H/2][W/2][Cout/8] words, one nibble per channel (channel c in bits 4*(c%8) of word c/8): bits 0-1
- * = position (2*dy + dx) of the FIRST maximum of the 2x2 window in ATen's scan order, bit 2 = the
- * pooled value is > 0 (ReLU gate).  With the codes the full-resolution activation has no reader
- * left in the backward pass: out_post may be NULL (saves its write), and
- * stv_conv3x3_dgrad_unpool routes the gradient without a pool-backward kernel. */
+/* Same, also recording what autograd's max_pool2d + ReLU backward need: out_code [H][W][Cout/32]
+ * words, bit (c % 32) of word c / 32 = "the pooled gradient of channel c is routed to THIS pixel":
+ * the pixel holds the FIRST maximum of its 2x2 window in ATen's scan order and that maximum is > 0
+ * (ReLU gate); pixels of a row / column dropped by floor mode get 0.  With the codes the
+ * full-resolution activation has no reader left in the backward pass: out_post may be NULL (saves
+ * its write), and stv_conv3x3_dgrad_unpool routes the gradient without a pool-backward kernel. */
 int stv_conv3x3_fwd_pool_code(const float* x, const float* w_fwd, const float* bias, int H, int W,
                               int Cin, int Cout, float* out_pre, float* out_post, float* out_pool,
                               unsigned* out_code, int round_pre, void* stream);
@@ -92,9 +92,19 @@ int stv_conv3x3_dgrad(const float* dy, const float* w_dgrad, int H, int W, int C
  * gated activation; [H][W][Cin/32]); relu_bits may be NULL (no gating). */
 int stv_conv3x3_dgrad_bits(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                            const unsigned* relu_bits, int accumulate, float* dx, void* stream);
+/* stv_conv3x3_dgrad_bits fused with the Gram backward (stv_style_bwd) of the layer whose gradient it
+ * produces -- the gradient at a style-tapped conv output is  relu'(.) .* dgrad(dy) + grad_w * F S
+ * (core_model.py:234-264 through autograd):  dx = bits .* conv_transpose(dy) + grad_w[0] * feat * s.
+ * feat: that layer's NHWC features [H][W][Cin], s: its seed matrix from stv_gram_loss_fwd.  The 1x1
+ * contraction runs as a second TMEM accumulator of the same tiles (64- and 128-channel layers), so
+ * the style gradient never makes a round trip through memory; other shapes fall back to the two
+ * separate launches inside this call. */
+int stv_conv3x3_dgrad_bits_style(const float* dy, const float* w_dgrad, int H, int W, int Cout,
+                                 int Cin, const unsigned* relu_bits, const float* feat,
+                                 const float* s, const float* grad_w, float* dx, void* stream);
 /* dgrad of the conv that FOLLOWS a MaxPool2d(2, 2), fused with the pool's (and the preceding
  * ReLU's) backward: dy [H][W][Cout] at pooled resolution, pool_code from
- * stv_conv3x3_fwd_pool_code ([H][W][Cin/8]), dx [H2][W2][Cin] at the resolution before the pool
+ * stv_conv3x3_fwd_pool_code ([H2][W2][Cin/32]), dx [H2][W2][Cin] at the resolution before the pool
  * (H = H2/2, W = W2/2, floor).  Every pooled gradient value is written to the recorded argmax
  * position of its window (zero elsewhere, zero everywhere when the gate bit is clear).  A last row /
  * column of dx dropped by floor mode is NOT written: allocate dx zero-filled. */

@@ -32,6 +32,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_conv3x3_fwd_bits": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_fwd_pool_code": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_dgrad_bits": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "stv_conv3x3_dgrad_bits_style": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "stv_conv3x3_dgrad_unpool": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp],
     "stv_conv3x3_fwd_pool": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_dgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],

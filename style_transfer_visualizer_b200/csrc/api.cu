@@ -186,6 +186,23 @@ int stv_conv3x3_dgrad_bits(const float* dy, const float* w_dgrad, int H, int W, 
   a.mask_bits = relu_bits;
   return conv_igemm2_launch(a, S(stream));
 }
+int stv_conv3x3_dgrad_bits_style(const float* dy, const float* w_dgrad, int H, int W, int Cout,
+                                 int Cin, const unsigned* relu_bits, const float* feat,
+                                 const float* s, const float* grad_w, float* dx, void* stream) {
+  STV_REQUIRE(feat && s && grad_w, "stv_conv3x3_dgrad_bits_style: feat, s and grad_w are required");
+  ConvArgs a = dgrad_args(dy, w_dgrad, H, W, Cout, Cin, 0, dx);
+  a.mask_bits = relu_bits;
+  a.style_x = feat;
+  a.style_s = s;
+  a.style_alpha = grad_w;
+  const int rc = conv_igemm2_launch(a, S(stream));
+  if (rc != kConvStyleNotFusable) return rc;
+  // tile family without the second accumulator (small feature maps): two launches, same result up
+  // to the order of the two additions
+  if (int rc2 = stv_style_bwd(feat, s, static_cast<long>(H) * W, Cin, grad_w, 0, dx, stream))
+    return rc2;
+  return stv_conv3x3_dgrad_bits(dy, w_dgrad, H, W, Cout, Cin, relu_bits, 1, dx, stream);
+}
 int stv_conv3x3_dgrad_unpool(const float* dy, const float* w_dgrad, int H, int W, int Cout, int Cin,
                              const unsigned* pool_code, int H2, int W2, float* dx, void* stream) {
   STV_REQUIRE(pool_code != nullptr, "stv_conv3x3_dgrad_unpool: pool_code is required");

@@ -63,13 +63,21 @@ struct Conv2Params {
   // ReLU / pool bookkeeping for the backward pass, so that it never re-reads an fp32 activation
   // just to test a sign or find an argmax:
   uint32_t* out_bits;          // forward: [H][W][N/32] words, bit c%32 = (out_post[.., c] > 0)
-  uint32_t* out_code;          // forward + fused pool: [H/2][W/2][N/8] words, one nibble per channel:
-                               // bits 0-1 = first-maximum position in the 2x2 window (ATen scan
-                               // order), bit 2 = pooled value > 0 (the ReLU gate)
+  uint32_t* out_code;          // forward + fused pool: [H][W][N/32] words, bit c%32 = "the pool + ReLU
+                               // backward routes the pooled gradient of channel c to THIS pixel"
+                               // (it holds the first maximum of its 2x2 window in ATen's scan
+                               // order, and that maximum is > 0)
   const uint32_t* mask_bits;   // dgrad: ReLU gate from out_bits of the gated layer (instead of mask_src)
   const uint32_t* unpool_code; // dgrad: the output is the gradient of a POOLED map; route it through
                                // the 2x2 max-pool (+ ReLU gate) straight into out_pre [H2][W2][N]
   int H2, W2;
+  // STYLE variant (dgrad of the conv that follows a style-tapped layer): the Gram backward
+  // dF = gl * F * S of the tapped layer is a SECOND accumulator of the same tile, fed by style_kc
+  // extra ring stages {F patch, S rows}; out = gate .* conv + gl * F S.  No separate 1x1 launch, no
+  // round trip of the style gradient through memory.
+  int style_kc;                // N / 32 slabs of the 1x1 contraction (0 = off)
+  int style_a_bytes;           // th * tw * 128: an F patch has no halo rows
+  const float* style_alpha;    // gl, device scalar
 #ifdef STV_EXPERIMENTS
   int debug;           // bottleneck experiments (results are then garbage): 1 skip weight loads,
                        // 2 skip activation loads, 4 skip stores, 8 skip MMAs
@@ -89,8 +97,11 @@ struct Conv2Params {
 #ifndef STV_EPI_WIDE
 #define STV_EPI_WIDE 1
 #endif
-__host__ __device__ constexpr int conv2_epi_warps(int block_n) {
-  return (STV_EPI_WIDE && block_n >= 128) ? 8 : 4;
+// 64-wide two-half tiles as well: with four warps the epilogue of a 256 x 64 tile (pool shuffles,
+// four-pixel un-pooling stores) took longer than its 144 MMAs and set the pace of conv1_2 forward
+// and conv2_1 dgrad at 1080p (profiles/r2_ncu_conv_gram_metrics_1080p_v1.csv: 22 % tensor active).
+__host__ __device__ constexpr int conv2_epi_warps(int block_n, int mh = 2) {
+  return (STV_EPI_WIDE && (block_n >= 128 || (block_n == 64 && mh == 2))) ? 8 : 4;
 }
 // Two-half tiles get one MMA-issuing thread PER HALF (its own accumulator, so no ordering between
 // them): tcgen05.commit stalls its thread for ~500 cycles, which starves the tensor pipe when a
@@ -98,24 +109,30 @@ __host__ __device__ constexpr int conv2_epi_warps(int block_n) {
 // (profiles/r1_umma_peak.log: N=64 72 -> 53 cycles per MMA, N=128 87 -> 66).
 __host__ __device__ constexpr int conv2_issuers(int mh) { return mh == 2 ? 2 : 1; }
 __host__ __device__ constexpr int conv2_threads(int block_n, int mh) {
-  return 32 * (1 + conv2_issuers(mh) + conv2_epi_warps(block_n));
+  return 32 * (1 + conv2_issuers(mh) + conv2_epi_warps(block_n, mh));
 }
 
-template <int BLOCK_N, int MH, bool PAIR>
+template <int BLOCK_N, int MH, bool PAIR, bool STYLE = false>
 struct Conv2Cfg {
-  static constexpr int kAcc = (2 * MH * BLOCK_N <= 512) ? 2 : 1;
-  static constexpr int kTmemColsRaw = kAcc * MH * BLOCK_N;
+  static constexpr int kAccW = STYLE ? 2 : 1;  // accumulators per 128-pixel half (conv, style)
+  static constexpr int kTileCols = MH * BLOCK_N * kAccW;
+  static constexpr int kAcc = (2 * kTileCols <= 512) ? 2 : 1;
+  static constexpr int kTmemColsRaw = kAcc * kTileCols;
   static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
   static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // weight rows staged by ONE CTA
   static constexpr int kBBytes = kBRows * 128;
 };
 
-template <int BLOCK_N, int MH, int TPS, bool PAIR>
-__global__ void __launch_bounds__(conv2_threads(BLOCK_N, MH), 1)
+// 64- and 16-wide one-half tiles run as two co-resident CTAs per SM: cap their registers accordingly
+template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false>
+__global__ void __launch_bounds__(conv2_threads(BLOCK_N, MH), (BLOCK_N <= 64 && MH == 1) ? 2 : 1)
 conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                        const __grid_constant__ CUtensorMap tmap_w, const Conv2Params p) {
-  using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR>;
-  constexpr int EW = conv2_epi_warps(BLOCK_N);
+                        const __grid_constant__ CUtensorMap tmap_w,
+                        const __grid_constant__ CUtensorMap tmap_f,
+                        const __grid_constant__ CUtensorMap tmap_s, const Conv2Params p) {
+  using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR, STYLE>;
+  constexpr int kTileCols = Cfg::kTileCols;
+  constexpr int EW = conv2_epi_warps(BLOCK_N, MH);
   constexpr int NI = conv2_issuers(MH);
   constexpr int kThreads2 = conv2_threads(BLOCK_N, MH);
   constexpr int kFirstEpiWarp = 1 + NI;
@@ -153,6 +170,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    if constexpr (STYLE) {
+      tma_prefetch_desc(&tmap_f);
+      tma_prefetch_desc(&tmap_s);
+    }
     // PAIR: the leader's "full" barriers collect one expect_tx arrival from each CTA's producer,
     // its "accumulator drained" barriers one arrival from each epilogue warp of both CTAs
     const uint32_t np = PAIR ? 2u : 1u;
@@ -261,6 +282,28 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             }
           }
         }
+        if constexpr (STYLE) {
+          // Gram backward of the tapped layer as extra K steps of the same tile: stage =
+          // {F patch (no halo), 32-channel slab of S rows n0..}; unified ring only
+          const uint32_t tx_s = static_cast<uint32_t>(p.style_a_bytes + Cfg::kBBytes);
+          for (int c = 0; c < p.style_kc; ++c) {
+            mbar_wait(a_empty + 8 * as, aph ^ 1);
+            const int cur = as;
+            if constexpr (PAIR) {
+              mbar_expect_tx_cluster(a_full_c + 8 * cur, tx_s);
+              tma_load_3d_pair(a_base + cur * p.a_stage_bytes, &tmap_f, a_full_c + 8 * cur, c << 5,
+                               tx0, ty0);
+              tma_load_2d_pair(b_base + cur * TPS * Cfg::kBBytes, &tmap_s, a_full_c + 8 * cur,
+                               c << 5, n0);
+            } else {
+              mbar_expect_tx(a_full + 8 * cur, tx_s);
+              tma_load_3d(a_base + cur * p.a_stage_bytes, &tmap_f, a_full + 8 * cur, c << 5, tx0,
+                          ty0);
+              tma_load_2d(b_base + cur * TPS * Cfg::kBBytes, &tmap_s, a_full + 8 * cur, c << 5, n0);
+            }
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+        }
       }
     }
   } else if (warp < kFirstEpiWarp) {
@@ -285,7 +328,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         if constexpr (PAIR) mbar_wait_cluster(acc_empty + 8 * acc, accph ^ 1);
         else mbar_wait(acc_empty + 8 * acc, accph ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * (MH * BLOCK_N);
+        const uint32_t d0 = tmem_base + acc * kTileCols;
         uint32_t accum = 0;
         for (int c = 0; c < kc; ++c) {
           for (int dxi = 0; dxi < ndx; ++dxi) {
@@ -330,6 +373,34 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             if (++as == AS) { as = 0; aph ^= 1; }
           }
         }
+        if constexpr (STYLE) {
+          // second accumulator of the tile (columns MH * BLOCK_N ..): F patch x S slab, K = N
+          for (int c = 0; c < p.style_kc; ++c) {
+            mbar_wait(a_full + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t a_lo = (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+            const uint32_t b_lo =
+                (((b_base + as * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
+#pragma unroll
+            for (int hf = hf0; hf < hf1; ++hf) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc =
+                    (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + hf * half16 + 2 * k);
+                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
+                if constexpr (PAIR)
+                  umma_tf32_pair(d0 + MH * BLOCK_N + hf * BLOCK_N, adesc, bdesc, idesc,
+                                 (c | k) != 0 ? 1u : 0u);
+                else
+                  umma_tf32(d0 + MH * BLOCK_N + hf * BLOCK_N, adesc, bdesc, idesc,
+                            (c | k) != 0 ? 1u : 0u);
+              }
+            }
+            if constexpr (PAIR) umma_commit_pair(a_empty + 8 * as);
+            else umma_commit(a_empty + 8 * as);
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+        }
         if constexpr (PAIR) umma_commit_pair(acc_full + 8 * acc);
         else umma_commit(acc_full + 8 * acc);
         if (++acc == kAcc) { acc = 0; accph ^= 1; }
@@ -358,7 +429,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         const int px = tx0 + (m & (p.tw - 1));
         const bool valid = (py < p.H) && (px < p.W) && !STV_DBG(p, 4);
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                              acc * (MH * BLOCK_N) + hf * BLOCK_N;
+                              acc * kTileCols + hf * BLOCK_N;
         if constexpr (BLOCK_N == 16) {
           uint32_t r[16];
           asm volatile(
@@ -384,7 +455,6 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             // and no pool-backward kernel re-reads the fp32 activation for its argmax.  Each lane
             // owns one pooled pixel and writes the four pixels of its window (zeros except at the
             // recorded first-maximum position), 128 contiguous bytes per pixel and chunk.
-            const size_t pix = static_cast<size_t>(py) * p.W + px;
             const size_t o00 = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * p.N + n0;
             const size_t wrow = static_cast<size_t>(p.W2) * p.N;
 #pragma unroll 1
@@ -393,9 +463,14 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               tmem_ld_32x32(trow + cb, r);
               tmem_ld_wait();
               if (!valid) continue;
-              const uint4 cw4 =
-                  __ldg(reinterpret_cast<const uint4*>(p.unpool_code + ((pix * p.N + n0 + cb) >> 3)));
-              const uint32_t cw[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
+              const size_t wq = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * (p.N >> 5) +
+                                ((n0 + cb) >> 5);
+              const size_t wrow_w = static_cast<size_t>(p.W2) * (p.N >> 5);
+              uint32_t rw[4];  // route bits of the four window pixels for these 32 channels
+              rw[0] = __ldg(p.unpool_code + wq);
+              rw[1] = __ldg(p.unpool_code + wq + (p.N >> 5));
+              rw[2] = __ldg(p.unpool_code + wq + wrow_w);
+              rw[3] = __ldg(p.unpool_code + wq + wrow_w + (p.N >> 5));
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 float v[4];
@@ -404,14 +479,14 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   v[e] = __uint_as_float(r[4 * j + e]) * alpha;
                   if (p.round_pre) v[e] = round_tf32(v[e]);
                 }
-                const uint32_t c16 = (cw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                  const uint32_t b4 = rw[q] >> (4 * j);
                   float4 o;
-                  o.x = ((c16 & 7u) == (4u | q)) ? v[0] : 0.f;
-                  o.y = (((c16 >> 4) & 7u) == (4u | q)) ? v[1] : 0.f;
-                  o.z = (((c16 >> 8) & 7u) == (4u | q)) ? v[2] : 0.f;
-                  o.w = (((c16 >> 12) & 7u) == (4u | q)) ? v[3] : 0.f;
+                  o.x = (b4 & 1u) ? v[0] : 0.f;
+                  o.y = (b4 & 2u) ? v[1] : 0.f;
+                  o.z = (b4 & 4u) ? v[2] : 0.f;
+                  o.w = (b4 & 8u) ? v[3] : 0.f;
                   const size_t off = o00 + (q >> 1) * wrow + (q & 1) * p.N + cb + 4 * j;
                   *reinterpret_cast<float4*>(p.out_pre + off) = o;
                 }
@@ -436,8 +511,9 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             // (a pooled layer's full-resolution activation has no reader once the backward pass
             // works from the pool codes)
             const bool want_post = p.out_post != nullptr || pool || p.out_bits != nullptr;
-            const bool odd_x = (px & 1) != 0;
+            const bool odd_x = (px & 1) != 0, odd_y = (py & 1) != 0;
             const int Ho = p.H >> 1, Wo = p.W >> 1;
+            const bool in_window = (py >> 1) < Ho && (px >> 1) < Wo;
             const bool pool_writer = pool && !(py & 1) && !(px & 1) && (py >> 1) < Ho &&
                                      (px >> 1) < Wo && !STV_DBG(p, 4);
             const size_t pool_off =
@@ -450,8 +526,15 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               uint32_t gate = 0xFFFFFFFFu;  // dgrad: ReLU gate of this pixel's 32 channels
               if (p.mask_bits != nullptr && valid)
                 gate = __ldg(p.mask_bits + pix * (p.N >> 5) + ((n0 + cb) >> 5));
+              uint32_t r2[STYLE ? 32 : 1];  // style accumulator chunk: gl * (F S)
+              float gl = 0.f;
+              if constexpr (STYLE) {
+                tmem_ld_32x32(trow + MH * BLOCK_N + cb, r2);
+                tmem_ld_wait();
+                gl = __ldg(p.style_alpha);
+              }
               uint32_t bits = 0;            // forward: sign bits of the post-ReLU values
-              uint32_t codew[4] = {0u, 0u, 0u, 0u};
+              uint32_t route = 0;           // forward + pool: pool / ReLU backward routing bits
               if (valid || pool) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -466,6 +549,12 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   v.y = (g4 & 2u) ? v.y : 0.f;
                   v.z = (g4 & 4u) ? v.z : 0.f;
                   v.w = (g4 & 8u) ? v.w : 0.f;
+                  if constexpr (STYLE) {  // the loss gradient of the tapped layer is not gated
+                    v.x = fmaf(__uint_as_float(r2[4 * j + 0]), gl, v.x);
+                    v.y = fmaf(__uint_as_float(r2[4 * j + 1]), gl, v.y);
+                    v.z = fmaf(__uint_as_float(r2[4 * j + 2]), gl, v.z);
+                    v.w = fmaf(__uint_as_float(r2[4 * j + 3]), gl, v.w);
+                  }
                   const int col = cb + 4 * j;
                   if (p.out_pre && valid) {
                     float4 o = v;
@@ -488,45 +577,36 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                     bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) |
                              (o.w > 0.f ? 8u : 0u)) << (4 * j);
                     if (pool) {  // warp-uniform branch: every lane takes part in the shuffles
-                      // x stage: (a, b) = (even-x pixel, odd-x pixel) of this row; strict > keeps the
-                      // first maximum, the scan order of ATen's max_pool2d (a, b, then the next row)
+                      // 2x2 window = lanes {l, l^1 (x neighbour), l^tw, l^tw^1 (next / previous
+                      // row)}: two shuffles per value give every lane the window maximum.  A lane
+                      // routes the pooled gradient iff it holds the FIRST maximum in ATen's scan
+                      // order (a, b, then the next row) and that maximum is positive (ReLU gate).
                       const float ov[4] = {o.x, o.y, o.z, o.w};
-                      float m0[4];
-                      uint32_t kb = 0;
+                      float mx[4];
+                      uint32_t rb = 0;
 #pragma unroll
                       for (int e = 0; e < 4; ++e) {
                         const float nb = __shfl_xor_sync(0xffffffffu, ov[e], 1);
-                        const float a = odd_x ? nb : ov[e];
-                        const float bb = odd_x ? ov[e] : nb;
-                        const bool k0 = (bb > a) || (bb != bb);  // ATen: (val > max) || isnan(val)
-                        m0[e] = k0 ? bb : a;
-                        kb |= (k0 ? 1u : 0u) << e;
-                      }
-                      // y stage: this lane acts as the top row (only the (even, even) lane stores)
-                      const uint32_t kbo = __shfl_xor_sync(0xffffffffu, kb, p.tw);
-                      float mx[4];
-                      uint32_t c16 = 0;
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        const float mo = __shfl_xor_sync(0xffffffffu, m0[e], p.tw);
-                        const bool lower = (mo > m0[e]) || (mo != mo);
-                        mx[e] = lower ? mo : m0[e];
-                        const uint32_t k = lower ? (2u | ((kbo >> e) & 1u)) : ((kb >> e) & 1u);
-                        c16 |= (k | (mx[e] > 0.f ? 4u : 0u)) << (4 * e);
+                        const float m0 = (nb > ov[e] || nb != nb) ? nb : ov[e];  // row maximum
+                        const float mo = __shfl_xor_sync(0xffffffffu, m0, p.tw);
+                        const float m = (mo > m0 || mo != mo) ? mo : m0;
+                        mx[e] = m;
+                        const bool first = (ov[e] == m) && (m > 0.f) && !(odd_x && nb == m) &&
+                                           !(odd_y && mo == m);
+                        rb |= (first ? 1u : 0u) << e;
                       }
                       if (pool_writer)
                         *reinterpret_cast<float4*>(p.out_pool + pool_off + col) =
                             make_float4(mx[0], mx[1], mx[2], mx[3]);
-                      if (want_code) codew[j >> 1] |= c16 << (16 * (j & 1));
+                      route |= rb << (4 * j);
                     }
                   }
                 }
               }
               if (p.out_bits != nullptr && valid)
                 p.out_bits[pix * (p.N >> 5) + ((n0 + cb) >> 5)] = bits;
-              if (want_code && pool_writer)
-                *reinterpret_cast<uint4*>(p.out_code + ((pool_off + cb) >> 3)) =
-                    make_uint4(codew[0], codew[1], codew[2], codew[3]);
+              if (want_code && valid)  // pixels of a row / column dropped by floor mode route nothing
+                p.out_code[pix * (p.N >> 5) + ((n0 + cb) >> 5)] = in_window ? route : 0u;
             }
             continue;
           }
@@ -678,17 +758,18 @@ static int current_device() {
 // b_rows: weight rows one CTA stages per tap (the N tile, or half of it for a CTA pair)
 // staging: the transposing epilogue (ReLU gate / accumulate) needs one 4 KB tile per epilogue warp
 static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int b_rows,
-                            int n_total, int block_n, int staging) {
+                            int n_total, int block_n, int mh, int staging) {
   return as * a_stage_bytes + bs * tps * b_rows * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
-         n_total * 4 + 128 + (staging ? conv2_epi_warps(block_n) * 4096 : 0);
+         n_total * 4 + 128 + (staging ? conv2_epi_warps(block_n, mh) * 4096 : 0);
 }
 
-template <int BLOCK_N, int MH, int TPS, bool PAIR>
+template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false>
 static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Params& p, int grid,
-                   cudaStream_t stream) {
-  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR>;
+                   cudaStream_t stream, const CUtensorMap* tf = nullptr,
+                   const CUtensorMap* ts = nullptr) {
+  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR, STYLE>;
   const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
-                                    Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N,
+                                    Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N, MH,
                                     p.mask_src != nullptr || p.add_src != nullptr);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   const int dev = current_device();
@@ -735,7 +816,8 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
     }
     if (grid > 2 * max_clusters[dev]) cfg.gridDim = dim3(2 * max_clusters[dev]);
   }
-  STV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, p));
+  // kernels without the STYLE accumulator ignore the two extra descriptors
+  STV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tf ? *tf : tx, ts ? *ts : tw, p));
   return 0;
 }
 
@@ -833,6 +915,14 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
     STV_REQUIRE(static_cast<double>(a.H2) * a.W2 * N < 4.0e9, "conv_igemm2: un-pooled tensor too large");
   }
 
+  const bool style = a.style_x != nullptr;
+  if (style) {
+    STV_REQUIRE(a.style_s != nullptr && a.style_alpha != nullptr && taps == 9 && N != 16 &&
+                    a.out_pre != nullptr && a.out_post == nullptr && !a.mask_src && !a.add_src &&
+                    !a.unpool_code && !a.out_pool && !a.bias && !a.alpha,
+                "conv_igemm2: the fused style backward is a dgrad option (gate bits only)");
+  }
+
   // big global reads in the epilogue (fp32 gate or accumulate source) go through the transposing
   // path; it also selects one-half tiles for the 64-wide layers (two co-resident CTAs)
   const bool staging = a.mask_src != nullptr || a.add_src != nullptr;
@@ -859,6 +949,14 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   p.mask_bits = a.mask_bits;
   p.unpool_code = a.unpool_code;
   p.H2 = a.H2; p.W2 = a.W2;
+  p.style_kc = style ? N / 32 : 0;
+  p.style_a_bytes = tc.th * tc.tw * 128;
+  p.style_alpha = a.style_alpha;
+  // the second accumulator exists for the two tile families the tapped 64- and 128-wide layers
+  // use; any other choice (small feature maps narrow the tile) reports "not fusable" to the caller
+  if (style && !((tc.block_n == 64 && tc.mh == 1 && !tc.pair) ||
+                 (tc.block_n == 128 && tc.mh == 2 && tc.pair)))
+    return kConvStyleNotFusable;
   STV_REQUIRE(a.out_code == nullptr || p.out_code != nullptr,
               "conv_igemm2: pool codes requested but the pool cannot be fused for this shape");
 #ifdef STV_EXPERIMENTS
@@ -881,6 +979,17 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
     const uint32_t box[2] = {32, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n)};
     if (int rc = encode_tmap_f32(&twm, a.w_packed, 2, dims, strides, box, kSwizzle128B)) return rc;
   }
+  CUtensorMap tf, ts;
+  if (style) {
+    const uint64_t dims[3] = {(uint64_t)N, (uint64_t)W, (uint64_t)H};
+    const uint64_t strides[2] = {(uint64_t)N * 4, (uint64_t)W * N * 4};
+    const uint32_t box[3] = {32, (uint32_t)tc.tw, (uint32_t)tc.th};
+    if (int rc = encode_tmap_f32(&tf, a.style_x, 3, dims, strides, box, kSwizzle128B)) return rc;
+    const uint64_t sdims[2] = {(uint64_t)N, (uint64_t)N};
+    const uint64_t sstrides[1] = {(uint64_t)N * 4};
+    const uint32_t sbox[2] = {32, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n)};
+    if (int rc = encode_tmap_f32(&ts, a.style_s, 2, sdims, sstrides, sbox, kSwizzle128B)) return rc;
+  }
   const int sms = device_sm_count();
   // ring depths: defaults keep >= ~2000 MMA cycles of weight stages in flight (TMA latency under
   // load) within the shared-memory budget; stv_conv_set_tuning overrides them for sweeps
@@ -895,7 +1004,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
     int depth = (tc.block_n == 64 && tc.mh == 1) ? 2 : 4;
     if (env_as > 0) depth = env_as;
     while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, depth, depth, p.tps, b_rows, N,
-                                         tc.block_n, staging) > 227 * 1024)
+                                         tc.block_n, tc.mh, staging) > 227 * 1024)
       --depth;
     p.a_stages = depth;
     p.b_stages = depth;
@@ -906,19 +1015,25 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
     if (env_as > 0) p.a_stages = env_as;
     if (env_bs > 0) p.b_stages = env_bs;
     while (conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N,
-                            tc.block_n, staging) > 227 * 1024 && p.b_stages > 2)
+                            tc.block_n, tc.mh, staging) > 227 * 1024 && p.b_stages > 2)
       --p.b_stages;
   }
   const int smem_est =
       conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N, tc.block_n,
-                       staging);
-  const int tmem_cols = (2 * tc.mh * tc.block_n <= 512 ? 2 : 1) * tc.mh * tc.block_n;
+                       tc.mh, staging);
+  const int tile_cols = tc.mh * tc.block_n * (style ? 2 : 1);
+  const int tmem_cols = (2 * tile_cols <= 512 ? 2 : 1) * tile_cols;
+  if (style && !(p.uni && p.tps == 3)) return kConvStyleNotFusable;  // tuning overrides
   const int ctas_per_sm = (smem_est <= 113 * 1024 && tmem_cols <= 256) ? 2 : 1;
   const int work_ctas = tc.pair ? 2 * p.tiles_total : p.tiles_total;
   int grid = work_ctas < sms * ctas_per_sm ? work_ctas : sms * ctas_per_sm;
   if (tc.pair) grid &= ~1;
 
   auto dispatch = [&]() -> int {
+  if (style) {
+    if (tc.block_n == 64) return launch2<64, 1, 3, false, true>(tx, twm, p, grid, stream, &tf, &ts);
+    return launch2<128, 2, 3, true, true>(tx, twm, p, grid, stream, &tf, &ts);
+  }
 #define STV_L2(BN, MHV)                                                          \
   if (tc.block_n == BN && tc.mh == MHV && !tc.pair) {                            \
     if (p.tps == 3) return launch2<BN, MHV, 3, false>(tx, twm, p, grid, stream); \

@@ -24,12 +24,20 @@ struct ConvArgs {
   float* out_nchw3 = nullptr;
   float* out_pool = nullptr;            // fused 2x2 max pool of the post-ReLU output
   unsigned* out_bits = nullptr;         // [H][W][N/32] sign bits of the post-ReLU output
-  unsigned* out_code = nullptr;         // [H/2][W/2][N/8] pool argmax + gate nibbles
+  unsigned* out_code = nullptr;         // [H][W][N/32] pool + ReLU backward routing bits
   const unsigned* mask_bits = nullptr;  // ReLU gate as bits (instead of mask_src)
   const unsigned* unpool_code = nullptr;  // route the result through the 2x2 pool backward
   int H2 = 0, W2 = 0;                   // un-pooled output size (unpool_code)
+  // dgrad + Gram backward of the layer whose gradient is being produced, as a second accumulator:
+  // out = gate .* conv + style_alpha[0] * style_x * style_s   (style_x: NHWC [H][W][N] features of
+  // that layer, style_s: symmetric [N][N] seed matrix)
+  const float* style_x = nullptr;
+  const float* style_s = nullptr;
+  const float* style_alpha = nullptr;
   int force_n = 0, force_mh = 0, force_tw = 0;
 };
+// returned (nothing launched) when the tile family chosen for this shape has no second accumulator
+constexpr int kConvStyleNotFusable = 3;
 int conv_igemm2_launch(const ConvArgs& args, cudaStream_t stream);
 
 // Thread-local tile-policy overrides (tests and sweeps).  pair_mode -1: built-in rule table; 0:

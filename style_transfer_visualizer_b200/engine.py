@@ -24,6 +24,7 @@ from . import ops
 # Default of VggLossEngine.compact_backward for engines created from now on (A/B measurements flip it
 # before building a model).
 DEFAULT_COMPACT_BACKWARD = True
+DEFAULT_FUSE_STYLE_BWD = True
 
 
 def _on_own_device(method):  # noqa: ANN001, ANN202
@@ -104,6 +105,7 @@ class VggLossEngine:
         # kernel, no full-resolution activation kept for pooled layers).  False = fp32 re-reads, kept
         # for A/B measurements; stages whose ReLU / pool output is tapped by a loss always use those.
         self.compact_backward = DEFAULT_COMPACT_BACKWARD
+        self.fuse_style_bwd = DEFAULT_FUSE_STYLE_BWD
 
     # ------------------------------------------------------------------ program construction
     def _build_stages(self, layers: list[nn.Module]) -> list[_Stage]:
@@ -224,6 +226,14 @@ class VggLossEngine:
         st = self.stages[s]
         return (self.compact_backward and st.relu_idx is not None and st.pool_idx is None
                 and st.relu_idx not in self._tapped and s + 1 < len(self.stages))
+
+    def _fuses_style_bwd(self, s: int) -> bool:
+        """Stage ``s``: conv output tapped by a style loss only, gated by sign bits, 64 or 128
+        channels wide -- its Gram backward runs as a second accumulator of the next layer's dgrad."""
+        st = self.stages[s]
+        return (self._uses_bits(s) and st.conv_idx in self.style_idx
+                and st.conv_idx not in self.content_idx and st.cout in (64, 128)
+                and self.fuse_style_bwd)
 
     def _uses_unpool(self, s: int) -> bool:
         """Stage ``s`` = conv -> ReLU -> pool with no loss tap, feeding another conv: the pool + ReLU
@@ -437,7 +447,8 @@ class VggLossEngine:
                 for s in range(n - 1, -1, -1):
                     st = self.stages[s]
                     tap_post = st.relu_idx is not None and st.relu_idx in self._tapped
-                    if st.pool_idx is None and not tap_post and st.conv_idx in self._tapped:
+                    if st.pool_idx is None and not tap_post and st.conv_idx in self._tapped \
+                            and not self._fuses_style_bwd(s):
                         self._tap_grads(ws, st.conv_idx, ws.pre[s], ws.d_y[s], grad_w, False)
                         done = torch.cuda.Event()
                         done.record(self._side)
@@ -472,6 +483,12 @@ class VggLossEngine:
                         ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_post, accumulate=acc)
                     acc2 = self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
                     ops.relu_bwd(d_post, ws.post[s], d_y, accumulate=acc2)
+                elif self._fuses_style_bwd(s):
+                    # ReLU gate, dgrad and this layer's Gram backward in ONE launch
+                    k = self.style_idx.index(st.conv_idx)
+                    ops.conv3x3_dgrad_style(ws.d_y[s + 1], down.w_dgrad, d_y, relu_bits=ws.bits[s],
+                                            feat=ws.pre[s], s_mat=ws.s_mat[k],
+                                            grad_w=grad_w[k:k + 1])
                 else:
                     if s in early:
                         main.wait_event(early[s])

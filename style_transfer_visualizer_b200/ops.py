@@ -40,8 +40,8 @@ def relu_bits_buffer(h: int, w: int, channels: int, device: torch.device) -> tor
 
 
 def pool_code_buffer(h: int, w: int, channels: int, device: torch.device) -> torch.Tensor:
-    """``[H/2, W/2, C/8]`` int32 words: pool argmax + ReLU gate nibbles (``stv_conv3x3_fwd_pool_code``)."""
-    return torch.empty(h // 2, w // 2, channels // 8, device=device, dtype=torch.int32)
+    """``[H, W, C/32]`` int32 words: pool + ReLU backward routing bits (``stv_conv3x3_fwd_pool_code``)."""
+    return torch.empty(h, w, channels // 32, device=device, dtype=torch.int32)
 
 
 def conv3x3_first_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
@@ -100,6 +100,18 @@ def conv3x3_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, dx: torch.Tensor,
         return
     nat.call("stv_conv3x3_dgrad", nat.ptr(dy), nat.ptr(w_dgrad), h, wd, cout, cin,
              nat.ptr(relu_src), int(accumulate), nat.ptr(dx), _s(dy))
+
+
+def conv3x3_dgrad_style(dy: torch.Tensor, w_dgrad: torch.Tensor, dx: torch.Tensor, *,  # noqa: PLR0913
+                        relu_bits: torch.Tensor | None, feat: torch.Tensor, s_mat: torch.Tensor,
+                        grad_w: torch.Tensor) -> None:
+    """``dx = bits .* dgrad(dy) + grad_w * feat @ s_mat``: conv input gradient and the Gram backward of
+    the style-tapped layer in one launch (``stv_conv3x3_dgrad_bits_style``)."""
+    _chk(dy, "dy")
+    h, wd, cout = dy.shape
+    cin = w_dgrad.shape[1]
+    nat.call("stv_conv3x3_dgrad_bits_style", nat.ptr(dy), nat.ptr(w_dgrad), h, wd, cout, cin,
+             nat.ptr(relu_bits), nat.ptr(feat), nat.ptr(s_mat), nat.ptr(grad_w), nat.ptr(dx), _s(dy))
 
 
 def conv3x3_dgrad_unpool(dy: torch.Tensor, w_dgrad: torch.Tensor, pool_code: torch.Tensor,

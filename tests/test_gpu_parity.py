@@ -62,8 +62,10 @@ GATES: dict[str, dict[str, float]] = {
     "lbfgs_random_64": {"layer_style_rel_max": 0.00049, "grad_rel_l2": 0.013},
     "lbfgs_noisy_64": {"layer_style_rel_max": 0.002, "grad_rel_l2": 0.02},
 }
-LBFGS_NOISY_RTOL = 0.15    # to be tightened to 1.5 x measured
-LBFGS_NOISY_FINAL = 0.05
+# lbfgs_noisy_64, per step: 1.5 x measured (profiles/r2_parity_lbfgs.log: 3e-4 3e-4 5.0e-2 7e-4 2e-4
+# 8.2e-3 6.0e-3 4.3e-3); step 3 is the first step built from a curvature pair (see module docstring)
+LBFGS_NOISY_RTOL = np.array([2e-3, 2e-3, 7.5e-2, 2e-3, 2e-3, 1.3e-2, 1.3e-2, 1.3e-2])
+LBFGS_NOISY_FINAL = 1.1e-2   # measured 7.3e-3
 CEILINGS = {"layer_style_rel_max": 2e-3, "grad_rel_l2": 3.5e-2, "total_rel_max": 2e-2,
             "style_rel_max": 3e-3, "final_rel_l2": 2e-2, "frames_max_lsb": 3,
             "frames_frac_diff": 0.15}
@@ -121,10 +123,12 @@ def test_lbfgs_first_steps_match_reference(name: str, cuda_device) -> None:  # n
         # the reference's DEFAULT optimiser pinned over the whole 8-step run, eagerly and through
         # the device-resident graph-captured step
         assert len(res.total) == 8
-        np.testing.assert_allclose(res.total, gold["total_loss"], rtol=LBFGS_NOISY_RTOL)
+        err = np.abs(np.array(res.total) - gold["total_loss"]) / np.abs(gold["total_loss"])
+        assert (err <= LBFGS_NOISY_RTOL).all(), err
         assert m["final_rel_l2"] <= LBFGS_NOISY_FINAL
         res_g = _gpu_run.run_case(cfg, cuda_device, use_cuda_graph=True)
-        np.testing.assert_allclose(res_g.total, gold["total_loss"], rtol=LBFGS_NOISY_RTOL)
+        err_g = np.abs(np.array(res_g.total) - gold["total_loss"]) / np.abs(gold["total_loss"])
+        assert (err_g <= LBFGS_NOISY_RTOL).all(), err_g
 
 
 def test_fused_lbfgs_tracks_torch_lbfgs(cuda_device) -> None:  # noqa: ANN001

@@ -412,10 +412,31 @@ def case_conv_compact() -> bool:
         sh = torch.arange(32, device=bits.device, dtype=torch.int32)
         return ((bits.unsqueeze(-1) >> sh) & 1).reshape(*bits.shape[:2], c).bool()
 
-    def unpack_code(code: torch.Tensor, c: int) -> torch.Tensor:
-        """[Ho, Wo, C/8] int32 -> [Ho, Wo, C] int (nibbles)."""
-        sh = torch.arange(0, 32, 4, device=code.device, dtype=torch.int32)
-        return ((code.unsqueeze(-1) >> sh) & 15).reshape(*code.shape[:2], c)
+    def route_reference(post: torch.Tensor) -> torch.Tensor:
+        """[H, W, C] bool: pixel receives the pooled gradient (first maximum of its 2x2 window in
+        ATen's scan order, maximum > 0); rows / columns dropped by floor mode route nothing."""
+        hh, ww, c = post.shape
+        ho, wo = hh // 2, ww // 2
+        win = post[:2 * ho, :2 * wo].reshape(ho, 2, wo, 2, c).permute(0, 2, 4, 1, 3) \
+            .reshape(ho, wo, c, 4)                               # window order a, b, d, e
+        k = torch.zeros(ho, wo, c, device=post.device, dtype=torch.int64)
+        m = win[..., 0].clone()
+        for q in (1, 2, 3):
+            better = win[..., q] > m
+            k = torch.where(better, torch.full_like(k, q), k)
+            m = torch.where(better, win[..., q], m)
+        hit = torch.nn.functional.one_hot(k, 4).bool() & (m > 0).unsqueeze(-1)   # [ho, wo, c, 4]
+        out = torch.zeros(hh, ww, c, device=post.device, dtype=torch.bool)
+        out[:2 * ho, :2 * wo] = hit.reshape(ho, wo, c, 2, 2).permute(0, 3, 1, 4, 2) \
+            .reshape(2 * ho, 2 * wo, c)
+        return out
+
+    def pack_bits(mask: torch.Tensor) -> torch.Tensor:
+        """[H, W, C] bool -> [H, W, C/32] int32 words."""
+        hh, ww, c = mask.shape
+        sh = torch.arange(32, device=mask.device, dtype=torch.int64)
+        packed = (mask.reshape(hh, ww, c // 32, 32).long() << sh).sum(-1)
+        return torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).int().contiguous()
 
     # first layer: bits of conv1_1's post
     for (hh, ww) in [(64, 64), (33, 47), (70, 94)]:
@@ -451,31 +472,20 @@ def case_conv_compact() -> bool:
             ops.conv3x3_fwd(xx, wf, bb, None, post2, out_bits=bits)
             same = torch.equal(post, post2) and torch.equal(unpack_bits(bits, co), post > 0)
             ok &= report(f"fwd + sign bits {tag}", 0.0 if same else 1.0, 0.0)
-            # ---- forward: pool + codes, post not stored
+            # ---- forward: pool + routing bits, post not stored
             ho, wo = hh // 2, ww // 2
             pool = torch.full((ho, wo, co), float("nan"), device=dev)
-            code = torch.full((ho, wo, co // 8), -1, device=dev, dtype=torch.int32)
+            code = torch.full((hh, ww, co // 32), -1, device=dev, dtype=torch.int32)
             ops.conv3x3_fwd(xx, wf, bb, None, None, out_pool=pool, out_code=code)
             pool_ref = torch.empty_like(pool)
             ops.maxpool2_fwd(post, pool_ref)
-            win = post[:2 * ho, :2 * wo].reshape(ho, 2, wo, 2, co).permute(0, 2, 4, 1, 3) \
-                .reshape(ho, wo, co, 4)                       # window order a, b, d, e
-            k = torch.zeros(ho, wo, co, device=dev, dtype=torch.int64)
-            m = win[..., 0].clone()
-            for q in (1, 2, 3):
-                better = win[..., q] > m
-                k = torch.where(better, torch.full_like(k, q), k)
-                m = torch.where(better, win[..., q], m)
-            nib_ref = k + 4 * (m > 0)
-            same = torch.equal(pool, pool_ref) and torch.equal(unpack_code(code, co).long(), nib_ref)
-            ok &= report(f"fwd + pool + codes {tag}", 0.0 if same else 1.0, 0.0)
+            same = torch.equal(pool, pool_ref) and torch.equal(unpack_bits(code, co),
+                                                               route_reference(post))
+            ok &= report(f"fwd + pool + route bits {tag}", 0.0 if same else 1.0, 0.0)
             # ---- dgrad gated by bits == dgrad gated by the fp32 activation (layer gated: [hh,ww,ci])
             dy = torch.randn(hh, ww, co, device=dev, generator=g)
             act = torch.randn(hh, ww, ci, device=dev, generator=g).relu()
-            abits = torch.zeros(hh, ww, ci // 32, device=dev, dtype=torch.int32)
-            sh = torch.arange(32, device=dev, dtype=torch.int64)
-            packed = ((act > 0).reshape(hh, ww, ci // 32, 32).long() << sh).sum(-1)
-            abits.copy_(torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).int())
+            abits = pack_bits(act > 0)
             if ci % 64 == 0:
                 prev = torch.randn(hh, ww, ci, device=dev, generator=g)
                 for accumulate in (False, True):
@@ -497,19 +507,7 @@ def case_conv_compact() -> bool:
         wt = torch.randn(cnext, cpool, 3, 3, device=dev, generator=g) * 0.05
         _wf, wd = ops.pack_conv_weights(wt)
         dy = torch.randn(ho, wo, cnext, device=dev, generator=g)
-        # codes from the reference definition (first maximum in scan order, gate = max > 0)
-        win = post[:2 * ho, :2 * wo].reshape(ho, 2, wo, 2, cpool).permute(0, 2, 4, 1, 3) \
-            .reshape(ho, wo, cpool, 4)
-        k = torch.zeros(ho, wo, cpool, device=dev, dtype=torch.int64)
-        m = win[..., 0].clone()
-        for q in (1, 2, 3):
-            better = win[..., q] > m
-            k = torch.where(better, torch.full_like(k, q), k)
-            m = torch.where(better, win[..., q], m)
-        nib = k + 4 * (m > 0)
-        sh4 = torch.arange(0, 32, 4, device=dev, dtype=torch.int64)
-        packed = (nib.reshape(ho, wo, cpool // 8, 8) << sh4).sum(-1)
-        code = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).int().contiguous()
+        code = pack_bits(route_reference(post))
         for pair_mode in (-1, 0, 1):
             ops.conv_set_tuning(pair_mode)
             d_pool = torch.empty(ho, wo, cpool, device=dev)
@@ -521,52 +519,85 @@ def case_conv_compact() -> bool:
             ok &= report(f"dgrad + unpool {h2}x{w2} {cnext}->{cpool} pair_mode={pair_mode}",
                          0.0 if torch.equal(got, want) else 1.0, 0.0)
         ops.conv_set_tuning()
+    # ---- dgrad + ReLU gate + Gram backward of the tapped layer in one launch (second accumulator)
+    # == style_bwd followed by the accumulating dgrad, up to fp32 rounding of the final addition
+    for (hh, ww, cn, cd) in [(64, 96, 64, 64), (135, 240, 64, 64), (70, 94, 128, 128),
+                             (200, 304, 128, 128), (24, 40, 128, 256), (33, 47, 64, 128)]:
+        dy = torch.randn(hh, ww, cd, device=dev, generator=g)
+        wt = torch.randn(cd, cn, 3, 3, device=dev, generator=g) * 0.05
+        _wf, wd = ops.pack_conv_weights(wt)
+        feat = torch.randn(hh, ww, cn, device=dev, generator=g)
+        sm = torch.randn(cn, cn, device=dev, generator=g) * 0.1
+        sm = (sm + sm.t()) * 0.5
+        gw = torch.tensor([3.0], device=dev)
+        abits = pack_bits(torch.rand(hh, ww, cn, device=dev, generator=g) > 0.4)
+        want = torch.empty(hh, ww, cn, device=dev)
+        ops.style_bwd(feat, sm, gw, want, accumulate=False)
+        ops.conv3x3_dgrad(dy, wd, want, relu_bits=abits, accumulate=True)
+        got = torch.full((hh, ww, cn), float("nan"), device=dev)
+        ops.conv3x3_dgrad_style(dy, wd, got, relu_bits=abits, feat=feat, s_mat=sm, grad_w=gw)
+        ok &= report(f"dgrad + gate + fused style bwd {hh}x{ww} {cd}->{cn}", rel_l2(got, want), 1e-3)
     torch.cuda.synchronize()
     return ok
 
 
 def case_halo() -> bool:
-    """stv_halo_exchange with three "ranks" emulated on ONE GPU: each rank is a stream, the
-    neighbours' peer pointers are ordinary device pointers of the same process.  The three exchange
-    launches are co-resident and hand-shake through the flag words exactly as across GPUs."""
+    """stv_halo_exchange on ONE GPU: the neighbours' buffers and flag words are ordinary device
+    memory of this process and their side of the hand-shake is played by the host (their flags are
+    raised before the launch), so the data path -- boundary rows pushed into the neighbours' halo
+    rows, zero padding at the image edge, multi-plane NCHW rows, unequal band sizes -- and the
+    flags this rank raises are checked exactly.  The concurrent hand-shake itself needs two GPUs
+    (tools/sharded_check.py): two mutually waiting kernels of one GPU can be serialised behind each
+    other by a shared hardware queue."""
     import torch
 
     from style_transfer_visualizer_b200 import ops
 
     dev = torch.device("cuda")
     ok = True
+    slot = 5
     for planes, rows_of, cols, ch in [(1, (8, 8, 6), 20, 64), (1, (5, 7, 3), 12, 128),
                                       (3, (16, 16, 12), 64, 1), (1, (4, 4, 4), 960, 64)]:
         n = len(rows_of)
         row_floats = cols * ch
-        bufs = [torch.zeros(planes, rows + 2, row_floats, device=dev) for rows in rows_of]
         flags = [torch.zeros(64 * 4, device=dev, dtype=torch.int32) for _ in range(n)]
         epoch = [torch.zeros(64, device=dev, dtype=torch.int32) for _ in range(n)]
         done = [torch.zeros(64, device=dev, dtype=torch.int32) for _ in range(n)]
-        streams = [torch.cuda.Stream() for _ in range(n)]
-        for it in range(3):
+        for it in range(1, 4):      # three epochs
             for r in range(n):
-                bufs[r].copy_(torch.randn(bufs[r].shape, device=dev))   # halos hold junk
-            want = [b.clone() for b in bufs]
-            for r in range(n):
-                want[r][:, 0] = want[r - 1][:, rows_of[r - 1]] if r > 0 else 0.0
-                want[r][:, rows_of[r] + 1] = bufs[r + 1][:, 1] if r < n - 1 else 0.0
-            torch.cuda.synchronize()
-            for r in range(n):
-                with torch.cuda.stream(streams[r]):
-                    ops.halo_exchange(
-                        bufs[r], up_ptr=bufs[r - 1].data_ptr() if r > 0 else None,
-                        down_ptr=bufs[r + 1].data_ptr() if r < n - 1 else None,
-                        rows=rows_of[r], rows_up=rows_of[r - 1] if r > 0 else 0,
-                        rows_down=rows_of[r + 1] if r < n - 1 else 0, row_floats=row_floats,
-                        planes=planes, flags_mine=flags[r],
-                        flags_up_ptr=flags[r - 1].data_ptr() if r > 0 else None,
-                        flags_down_ptr=flags[r + 1].data_ptr() if r < n - 1 else None,
-                        epoch=epoch[r], done=done[r], slot=5)
-            torch.cuda.synchronize()
-            same = all(torch.equal(bufs[r], want[r]) for r in range(n))
-            ok &= report(f"halo exchange planes={planes} rows={rows_of} row={row_floats} it={it}",
-                         0.0 if same else 1.0, 0.0)
+                bufs = [torch.randn(planes, rows + 2, row_floats, device=dev) for rows in rows_of]
+                before = [b.clone() for b in bufs]
+                flags[r][4 * slot:4 * slot + 4] = it        # the neighbours "have signalled"
+                torch.cuda.synchronize()
+                ops.halo_exchange(
+                    bufs[r], up_ptr=bufs[r - 1].data_ptr() if r > 0 else None,
+                    down_ptr=bufs[r + 1].data_ptr() if r < n - 1 else None,
+                    rows=rows_of[r], rows_up=rows_of[r - 1] if r > 0 else 0,
+                    rows_down=rows_of[r + 1] if r < n - 1 else 0, row_floats=row_floats,
+                    planes=planes, flags_mine=flags[r],
+                    flags_up_ptr=flags[r - 1].data_ptr() if r > 0 else None,
+                    flags_down_ptr=flags[r + 1].data_ptr() if r < n - 1 else None,
+                    epoch=epoch[r], done=done[r], slot=slot)
+                torch.cuda.synchronize()
+                want = [b.clone() for b in before]
+                if r > 0:
+                    want[r - 1][:, rows_of[r - 1] + 1] = before[r][:, 1]
+                else:
+                    want[r][:, 0] = 0.0
+                if r < n - 1:
+                    want[r + 1][:, 0] = before[r][:, rows_of[r]]
+                else:
+                    want[r][:, rows_of[r] + 1] = 0.0
+                same = all(torch.equal(bufs[k], want[k]) for k in range(n))
+                same = same and int(epoch[r][slot]) == it and int(done[r][slot]) == 0
+                if r > 0:       # A / B "from below" raised at the rank above
+                    same = same and flags[r - 1][4 * slot + 1].item() == it \
+                        and flags[r - 1][4 * slot + 3].item() == it
+                if r < n - 1:   # A / B "from above" raised at the rank below
+                    same = same and flags[r + 1][4 * slot + 0].item() == it \
+                        and flags[r + 1][4 * slot + 2].item() == it
+                ok &= report(f"halo push planes={planes} rows={rows_of} row={row_floats} rank={r} "
+                             f"epoch={it}", 0.0 if same else 1.0, 0.0)
     return ok
 
 
