@@ -75,6 +75,8 @@ struct Conv2Params {
   // dF = gl * F * S of the tapped layer is a SECOND accumulator of the same tile, fed by style_kc
   // extra ring stages {F patch, S rows}; out = gate .* conv + gl * F S.  No separate 1x1 launch, no
   // round trip of the style gradient through memory.
+  int staged;                  // plain / un-pooling epilogue stores go through the shared-memory
+                               // transpose (coalesced 128-byte lines); needs the staging tiles
   int style_kc;                // N / 32 slabs of the 1x1 contraction (0 = off)
   int style_a_bytes;           // th * tw * 128: an F patch has no halo rows
   const float* style_alpha;    // gl, device scalar
@@ -110,6 +112,39 @@ __host__ __device__ constexpr int conv2_epi_warps(int block_n, int mh = 2) {
 __host__ __device__ constexpr int conv2_issuers(int mh) { return mh == 2 ? 2 : 1; }
 __host__ __device__ constexpr int conv2_threads(int block_n, int mh) {
   return 32 * (1 + conv2_issuers(mh) + conv2_epi_warps(block_n, mh));
+}
+
+// One warp stores its 32 pixels x 32 channels (lane = pixel, v[32] = that pixel's values as raw
+// bits) through a 4 KB shared-memory tile: 16-byte chunks are written swizzled by (row & 7), read
+// back with 8 lanes per pixel, and every st.global.v4 instruction then covers 4 complete 128-byte
+// lines.  xform(bits, k) maps value k before it is staged; row_ptr(rr) is the global address of
+// pixel rr's 32-channel chunk, or nullptr when the pixel lies outside the image.
+template <class Xform, class RowPtr>
+__device__ __forceinline__ void staged_store_32x32(uint32_t stg, int lane, const uint32_t (&v)[32],
+                                                   Xform&& xform, RowPtr&& row_ptr) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(xform(v[4 * j], 4 * j)),
+                 "r"(xform(v[4 * j + 1], 4 * j + 1)), "r"(xform(v[4 * j + 2], 4 * j + 2)),
+                 "r"(xform(v[4 * j + 3], 4 * j + 3))
+                 : "memory");
+  }
+  __syncwarp();
+  const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + sub;
+    float* dst = row_ptr(rr);
+    const uint32_t a = stg + rr * 128 + ((chunk ^ (rr & 7)) << 4);
+    uint4 q4;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w)
+                 : "r"(a)
+                 : "memory");
+    if (dst != nullptr) *reinterpret_cast<uint4*>(dst + 4 * chunk) = q4;
+  }
+  __syncwarp();  // the staging tile is rewritten by the next call
 }
 
 template <int BLOCK_N, int MH, bool PAIR, bool STYLE = false>
@@ -449,12 +484,21 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             p.out_nchw3[2 * hw + o] = __uint_as_float(r[2]);
           }
         } else {
+          // Coalesced stores (p.staged): a warp's 32 pixels x 32 channels go through a 4 KB
+          // shared-memory tile so that every st.global.v4 covers four complete 128-byte lines (8
+          // lanes per pixel) instead of 32 different lines with 16 bytes each.  The scattered form
+          // costs ~4 LSU cycles per 16 bytes: with it a dual-output forward layer took 2.5x and an
+          // un-pooling dgrad 4x the time of the same MMAs (profiles/r2_epilogue_ab_v1.log).
+          constexpr bool kCanStage = BLOCK_N <= 128;  // wider tiles: no shared memory to spare
+          const bool staged = kCanStage && p.staged != 0;
+          const uint32_t stg = stage_base + (warp - kFirstEpiWarp) * 4096;
+          const int row_m0 = hf * 128 + q * 32;  // first pixel (tile-local) of this warp's 32 rows
           if (p.unpool_code != nullptr) {
             // dgrad whose output pixel is a POOLED pixel: the 2x2 max-pool backward (+ the ReLU gate
             // in front of the pool) is applied here, so the pooled gradient never goes to memory
             // and no pool-backward kernel re-reads the fp32 activation for its argmax.  Each lane
-            // owns one pooled pixel and writes the four pixels of its window (zeros except at the
-            // recorded first-maximum position), 128 contiguous bytes per pixel and chunk.
+            // owns one pooled pixel; the four pixels of its window receive the value or zero
+            // according to the routing bits the forward pass recorded.
             const size_t o00 = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * p.N + n0;
             const size_t wrow = static_cast<size_t>(p.W2) * p.N;
 #pragma unroll 1
@@ -462,43 +506,58 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               uint32_t r[32];
               tmem_ld_32x32(trow + cb, r);
               tmem_ld_wait();
-              if (!valid) continue;
-              const size_t wq = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * (p.N >> 5) +
-                                ((n0 + cb) >> 5);
-              const size_t wrow_w = static_cast<size_t>(p.W2) * (p.N >> 5);
-              uint32_t rw[4];  // route bits of the four window pixels for these 32 channels
-              rw[0] = __ldg(p.unpool_code + wq);
-              rw[1] = __ldg(p.unpool_code + wq + (p.N >> 5));
-              rw[2] = __ldg(p.unpool_code + wq + wrow_w);
-              rw[3] = __ldg(p.unpool_code + wq + wrow_w + (p.N >> 5));
+              uint32_t rw[4] = {0u, 0u, 0u, 0u};  // route bits of the four window pixels
+              if (valid) {
+                const size_t wq = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * (p.N >> 5) +
+                                  ((n0 + cb) >> 5);
+                const size_t wrow_w = static_cast<size_t>(p.W2) * (p.N >> 5);
+                rw[0] = __ldg(p.unpool_code + wq);
+                rw[1] = __ldg(p.unpool_code + wq + (p.N >> 5));
+                rw[2] = __ldg(p.unpool_code + wq + wrow_w);
+                rw[3] = __ldg(p.unpool_code + wq + wrow_w + (p.N >> 5));
+              }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float v[4];
+              for (int k = 0; k < 32; ++k) {
+                float v = __uint_as_float(r[k]) * alpha;
+                if (p.round_pre) v = round_tf32(v);
+                r[k] = __float_as_uint(v);
+              }
+              if (staged) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[e] = __uint_as_float(r[4 * j + e]) * alpha;
-                  if (p.round_pre) v[e] = round_tf32(v[e]);
+                for (int wq4 = 0; wq4 < 4; ++wq4) {
+                  const uint32_t bitsq = rw[wq4];
+                  staged_store_32x32(
+                      stg, lane, r,
+                      [&](uint32_t bits_v, int k) { return ((bitsq >> k) & 1u) ? bits_v : 0u; },
+                      [&](int rr) -> float* {
+                        const int mm = row_m0 + rr;
+                        const int yy = ty0 + (mm >> p.tw_shift), xx = tx0 + (mm & (p.tw - 1));
+                        if (yy >= p.H || xx >= p.W) return nullptr;
+                        return p.out_pre + (static_cast<size_t>(2 * yy + (wq4 >> 1)) * p.W2 +
+                                            2 * xx + (wq4 & 1)) * p.N + n0 + cb;
+                      });
                 }
+              } else if (valid) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint32_t b4 = rw[q] >> (4 * j);
-                  float4 o;
-                  o.x = (b4 & 1u) ? v[0] : 0.f;
-                  o.y = (b4 & 2u) ? v[1] : 0.f;
-                  o.z = (b4 & 4u) ? v[2] : 0.f;
-                  o.w = (b4 & 8u) ? v[3] : 0.f;
-                  const size_t off = o00 + (q >> 1) * wrow + (q & 1) * p.N + cb + 4 * j;
-                  *reinterpret_cast<float4*>(p.out_pre + off) = o;
+                for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                  for (int wq4 = 0; wq4 < 4; ++wq4) {
+                    const uint32_t b4 = rw[wq4] >> (4 * j);
+                    float4 o;
+                    o.x = (b4 & 1u) ? __uint_as_float(r[4 * j + 0]) : 0.f;
+                    o.y = (b4 & 2u) ? __uint_as_float(r[4 * j + 1]) : 0.f;
+                    o.z = (b4 & 4u) ? __uint_as_float(r[4 * j + 2]) : 0.f;
+                    o.w = (b4 & 8u) ? __uint_as_float(r[4 * j + 3]) : 0.f;
+                    const size_t off = o00 + (wq4 >> 1) * wrow + (wq4 & 1) * p.N + cb + 4 * j;
+                    *reinterpret_cast<float4*>(p.out_pre + off) = o;
+                  }
                 }
               }
             }
             continue;
           }
           if (p.mask_src == nullptr && p.add_src == nullptr) {
-            // Plain epilogue (forward; dgrad without accumulation): each lane owns one pixel row and
-            // writes its 32-channel chunk as eight 16-byte stores (the whole 128-byte line is
-            // produced back to back by one thread, which L2 merges); cheaper than the transpose
-            // when nothing but a sign word has to be read.
+            // Plain epilogue (forward; dgrad without accumulation): each lane owns one pixel row.
             const size_t pix = static_cast<size_t>(py) * p.W + px;
             const size_t row_off = pix * p.N + n0;
             // Fused max pool: the 2x2 window of a pooled pixel lives in four lanes of this warp
@@ -514,10 +573,16 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             const bool odd_x = (px & 1) != 0, odd_y = (py & 1) != 0;
             const int Ho = p.H >> 1, Wo = p.W >> 1;
             const bool in_window = (py >> 1) < Ho && (px >> 1) < Wo;
-            const bool pool_writer = pool && !(py & 1) && !(px & 1) && (py >> 1) < Ho &&
-                                     (px >> 1) < Wo && !STV_DBG(p, 4);
+            const bool pool_writer = pool && !(py & 1) && !(px & 1) && in_window && !STV_DBG(p, 4);
             const size_t pool_off =
                 (static_cast<size_t>(py >> 1) * Wo + (px >> 1)) * p.N + n0;
+            const bool direct = !staged;  // scattered 16-byte stores straight from the registers
+            auto row_ptr = [&](float* base, int cb, int rr) -> float* {
+              const int mm = row_m0 + rr;
+              const int yy = ty0 + (mm >> p.tw_shift), xx = tx0 + (mm & (p.tw - 1));
+              if (yy >= p.H || xx >= p.W || STV_DBG(p, 4)) return nullptr;
+              return base + (static_cast<size_t>(yy) * p.W + xx) * p.N + n0 + cb;
+            };
 #pragma unroll 1
             for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
               uint32_t r[32];
@@ -535,7 +600,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               }
               uint32_t bits = 0;            // forward: sign bits of the post-ReLU values
               uint32_t route = 0;           // forward + pool: pool / ReLU backward routing bits
-              if (valid || pool) {
+              if (valid || pool || staged) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + cb + 4 * j);
@@ -555,8 +620,11 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                     v.z = fmaf(__uint_as_float(r2[4 * j + 2]), gl, v.z);
                     v.w = fmaf(__uint_as_float(r2[4 * j + 3]), gl, v.w);
                   }
+                  // keep the (un-rounded) value for the staged stores below
+                  r[4 * j + 0] = __float_as_uint(v.x); r[4 * j + 1] = __float_as_uint(v.y);
+                  r[4 * j + 2] = __float_as_uint(v.z); r[4 * j + 3] = __float_as_uint(v.w);
                   const int col = cb + 4 * j;
-                  if (p.out_pre && valid) {
+                  if (direct && p.out_pre && valid) {
                     float4 o = v;
                     if (p.round_pre) {
                       o.x = round_tf32(o.x); o.y = round_tf32(o.y);
@@ -572,7 +640,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                       o.x = round_tf32(o.x); o.y = round_tf32(o.y);
                       o.z = round_tf32(o.z); o.w = round_tf32(o.w);
                     }
-                    if (p.out_post != nullptr && valid)
+                    if (direct && p.out_post != nullptr && valid)
                       *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
                     bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) |
                              (o.w > 0.f ? 8u : 0u)) << (4 * j);
@@ -607,6 +675,27 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                 p.out_bits[pix * (p.N >> 5) + ((n0 + cb) >> 5)] = bits;
               if (want_code && valid)  // pixels of a row / column dropped by floor mode route nothing
                 p.out_code[pix * (p.N >> 5) + ((n0 + cb) >> 5)] = in_window ? route : 0u;
+              if (staged) {
+                if (p.out_pre != nullptr) {
+                  const bool rnd = p.round_pre != 0;
+                  staged_store_32x32(
+                      stg, lane, r,
+                      [&](uint32_t bits_v, int) {
+                        return rnd ? __float_as_uint(round_tf32(__uint_as_float(bits_v))) : bits_v;
+                      },
+                      [&](int rr) { return row_ptr(p.out_pre, cb, rr); });
+                }
+                if (p.out_post != nullptr) {
+                  const bool rnd = p.round_post != 0;
+                  staged_store_32x32(
+                      stg, lane, r,
+                      [&](uint32_t bits_v, int) {
+                        const float o = relu_nan(__uint_as_float(bits_v));
+                        return __float_as_uint(rnd ? round_tf32(o) : o);
+                      },
+                      [&](int rr) { return row_ptr(p.out_post, cb, rr); });
+                }
+              }
             }
             continue;
           }
@@ -614,7 +703,6 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
           // global memory would touch 32 different 128-byte lines per instruction, 16 bytes each;
           // the tile is transposed through shared memory instead so that 8 lanes cover one
           // pixel's 128 bytes: every global load/store instruction moves 4 complete lines.
-          const uint32_t stg = stage_base + (warp - kFirstEpiWarp) * 4096;
           const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll 1
           for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
@@ -770,7 +858,7 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR, STYLE>;
   const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
                                     Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N, MH,
-                                    p.mask_src != nullptr || p.add_src != nullptr);
+                                    p.staged || p.mask_src != nullptr || p.add_src != nullptr);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   const int dev = current_device();
   // per kernel instantiation AND per device: the opt-in is a property of the (function, context)
@@ -925,9 +1013,9 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
 
   // big global reads in the epilogue (fp32 gate or accumulate source) go through the transposing
   // path; it also selects one-half tiles for the 64-wide layers (two co-resident CTAs)
-  const bool staging = a.mask_src != nullptr || a.add_src != nullptr;
-  const bool heavy = staging || a.mask_bits != nullptr;
-  const bool pool_ok = a.out_pool != nullptr && !staging && a.force_tw != 32;
+  const bool staging_needed = a.mask_src != nullptr || a.add_src != nullptr;
+  const bool heavy = staging_needed || a.mask_bits != nullptr;
+  const bool pool_ok = a.out_pool != nullptr && !staging_needed && a.force_tw != 32;
   const TileChoice tc = choose_tiles(a, heavy, pool_ok);
   Conv2Params p;
   p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps;
@@ -998,6 +1086,29 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   if (env_tps > 0 && taps == 9 && (tc.block_n <= 128 || tc.pair)) p.tps = env_tps;
   const int b_rows = tc.pair ? tc.block_n / 2 : tc.block_n;
   p.uni = (taps == 1 || p.tps == 3) ? 1 : 0;
+  // Coalesced epilogue stores need one 4 KB staging tile per epilogue warp.  The transposing
+  // (gate / accumulate) epilogue always has them; the plain and un-pooling epilogues of tiles up to
+  // 128 wide take them when that does not cost a ring stage (256-wide tiles are tensor-bound and
+  // their shared memory is full: they keep the direct stores).
+  bool staging = staging_needed;
+  p.staged = 0;
+  if (!staging_needed && N != 16 && tc.block_n <= 128) {
+    auto depth_for = [&](bool stg) {
+      int depth = p.uni ? ((tc.block_n == 64 && tc.mh == 1) ? 2 : 4) : 4;
+      if (p.uni && env_as > 0) depth = env_as;
+      const int a_st = p.uni ? 0 : (tc.block_n >= 256 ? 2 : 3);
+      while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, p.uni ? depth : a_st, depth, p.tps,
+                                           b_rows, N, tc.block_n, tc.mh, stg) > 227 * 1024)
+        --depth;
+      return depth;
+    };
+    if (p.uni && depth_for(true) == depth_for(false) &&
+        conv2_smem_bytes(p.a_stage_bytes, depth_for(true), depth_for(true), p.tps, b_rows, N,
+                         tc.block_n, tc.mh, true) <= 227 * 1024) {
+      staging = true;
+      p.staged = 1;
+    }
+  }
   if (p.uni) {
     // one ring of {A tile, its weight taps}: as deep as shared memory allows, up to 4; 64-wide and
     // 16-wide tiles stay at 2 so that two CTAs share an SM
