@@ -1092,7 +1092,13 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   // their shared memory is full: they keep the direct stores).
   bool staging = staging_needed;
   p.staged = 0;
-  if (!staging_needed && N != 16 && tc.block_n <= 128) {
+  // Measured per launch type (profiles/r2_epilogue_ab_v2.log): the transpose pays where a value is
+  // stored more than once or the epilogue is the bottleneck -- un-pooling dgrads (4 stores per value:
+  // 2.1-3.3x faster), dual-output forward layers (1.4-1.6x), single-output dgrads (+3-8 %) -- and
+  // costs 15-35 % on single-output forward layers, which therefore keep the direct stores.
+  const bool staged_pays = a.unpool_code != nullptr || (a.out_pre != nullptr && a.out_post != nullptr) ||
+                           (a.out_pre != nullptr && a.out_post == nullptr && a.out_pool == nullptr);
+  if (!staging_needed && staged_pays && N != 16 && tc.block_n <= 128) {
     auto depth_for = [&](bool stg) {
       int depth = p.uni ? ((tc.block_n == 64 && tc.mh == 1) ? 2 : 4) : 4;
       if (p.uni && env_as > 0) depth = env_as;
