@@ -125,6 +125,9 @@ int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream
 int stv_maxpool2_bwd(const float* dy, const float* x, int H, int W, int C, int relu_mask, float* dx,
                      void* stream);
 int stv_relu_fwd(const float* x, long n, float* y, void* stream);
+/* y = tf32(relu(x)) plus the sign bits of y (n / 32 words, as stv_conv3x3_fwd_bits records them): the
+ * ReLU of a loss-tapped layer whose conv stored only the pre-activation.  n % 32 == 0. */
+int stv_relu_fwd_bits(const float* x, long n, float* y, unsigned* bits, void* stream);
 int stv_relu_bwd(const float* dy, const float* x, long n, int accumulate, float* dx, void* stream);
 int stv_add_inplace(float* dst, const float* src, long n, void* stream);
 

@@ -41,6 +41,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_maxpool2_fwd": [_vp, _i, _i, _i, _vp, _vp],
     "stv_maxpool2_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "stv_relu_fwd": [_vp, _l, _vp, _vp],
+    "stv_relu_fwd_bits": [_vp, _l, _vp, _vp, _vp],
     "stv_relu_bwd": [_vp, _vp, _l, _i, _vp, _vp],
     "stv_add_inplace": [_vp, _vp, _l, _vp],
     "stv_gram_workspace_bytes": [_l, _i],

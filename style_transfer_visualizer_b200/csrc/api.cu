@@ -235,6 +235,9 @@ int stv_maxpool2_bwd(const float* dy, const float* x, int H, int W, int C, int r
 int stv_relu_fwd(const float* x, long n, float* y, void* stream) {
   return relu_fwd_launch(x, n, y, S(stream));
 }
+int stv_relu_fwd_bits(const float* x, long n, float* y, unsigned* bits, void* stream) {
+  return relu_fwd_bits_launch(x, n, y, bits, S(stream));
+}
 int stv_relu_bwd(const float* dy, const float* x, long n, int accumulate, float* dx, void* stream) {
   return relu_bwd_launch(dy, x, n, accumulate, dx, S(stream));
 }

@@ -139,6 +139,31 @@ __global__ void relu_fwd_kernel(const float4* __restrict__ x, long n4, float4* _
     y[i] = make_float4(relu_nan(v.x), relu_nan(v.y), relu_nan(v.z), relu_nan(v.w));
   }
 }
+// ReLU forward of a tapped layer's stored pre-activation, for layers whose conv epilogue would
+// otherwise write both tensors with scattered stores (256-wide tiles have no shared memory left
+// for coalescing them): y = tf32(relu(x)) -- the next conv's MMA operand -- and the sign bits the
+// dgrad gates with.  One thread = 4 channels; the 8 threads of a 32-channel word are adjacent lanes.
+__global__ void __launch_bounds__(256)
+relu_fwd_bits_kernel(const float4* __restrict__ x, long n4, float4* __restrict__ y,
+                     unsigned* __restrict__ bits) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const long stride = static_cast<long>(gridDim.x) * 256;
+  const long n4_up = (n4 + 255) & ~255L;  // whole warps iterate together (shuffles below)
+  for (long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x; i < n4_up; i += stride) {
+    const bool live = i < n4;
+    float4 v = live ? __ldg(x + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = round_tf32(relu_nan(v.x)); v.y = round_tf32(relu_nan(v.y));
+    v.z = round_tf32(relu_nan(v.z)); v.w = round_tf32(relu_nan(v.w));
+    if (live) y[i] = v;
+    unsigned nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) |
+                   (v.w > 0.f ? 8u : 0u);
+    nib <<= 4 * (threadIdx.x & 7);
+    nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+    nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+    nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+    if (live && (threadIdx.x & 7) == 0 && bits != nullptr) bits[i >> 3] = nib;
+  }
+}
 __global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                                 long n4, int accumulate, float4* dx) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -549,6 +574,13 @@ int relu_fwd_launch(const float* x, long n, float* y, cudaStream_t stream) {
   STV_REQUIRE(n % 4 == 0, "relu: n must be a multiple of 4");
   relu_fwd_kernel<<<grid_for(n / 4, 256, stream_blocks()), 256, 0, stream>>>(
       reinterpret_cast<const float4*>(x), n / 4, reinterpret_cast<float4*>(y));
+  STV_LAUNCH_CHECK();
+  return 0;
+}
+int relu_fwd_bits_launch(const float* x, long n, float* y, unsigned* bits, cudaStream_t stream) {
+  STV_REQUIRE(n % 32 == 0, "relu_fwd_bits: n must be a multiple of 32 (whole sign-bit words)");
+  relu_fwd_bits_kernel<<<grid_for(n / 4, 256, stream_blocks()), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), n / 4, reinterpret_cast<float4*>(y), bits);
   STV_LAUNCH_CHECK();
   return 0;
 }

@@ -70,6 +70,7 @@ int maxpool2_fwd_launch(const float* x, int H, int W, int C, float* y, cudaStrea
 int maxpool2_bwd_launch(const float* dy, const float* x, int H, int W, int C, int relu_mask,
                         float* dx, cudaStream_t stream);
 int relu_fwd_launch(const float* x, long n, float* y, cudaStream_t stream);
+int relu_fwd_bits_launch(const float* x, long n, float* y, unsigned* bits, cudaStream_t stream);
 int relu_bwd_launch(const float* dy, const float* x, long n, int accumulate, float* dx,
                     cudaStream_t stream);
 int add_inplace_launch(float* dst, const float* src, long n, cudaStream_t stream);

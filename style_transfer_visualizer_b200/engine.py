@@ -227,6 +227,11 @@ class VggLossEngine:
         return (self.compact_backward and st.relu_idx is not None and st.pool_idx is None
                 and st.relu_idx not in self._tapped and s + 1 < len(self.stages))
 
+    def _split_relu(self, s: int, ws: _Workspace) -> bool:
+        st = self.stages[s]
+        return (self.compact_backward and s > 0 and ws.pre[s] is not None and ws.post[s] is not None
+                and st.pool_idx is None and st.cout >= 256 and st.cout % 32 == 0)
+
     def _fuses_style_bwd(self, s: int) -> bool:
         """Stage ``s``: conv output tapped by a style loss only, gated by sign bits, 64 or 128
         channels wide -- its Gram backward runs as a second accumulator of the next layer's dgrad."""
@@ -299,6 +304,14 @@ class VggLossEngine:
                 ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], None,
                                 round_pre=self._round_pre(st), out_pool=ws.pool[s],
                                 out_code=ws.code[s])
+            elif self._split_relu(s, ws):
+                # 256-wide tiles cannot coalesce two output tensors (no shared memory left for the
+                # staging tiles) and a dual-output epilogue of scattered stores costs more than the
+                # whole MMA work of the layer: the conv stores the tapped pre-activation only, a
+                # memory-bound pass makes the ReLU'd operand + sign bits from it
+                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], None,
+                                round_pre=self._round_pre(st))
+                ops.relu_fwd_bits(ws.pre[s], ws.post[s], ws.bits[s])
             else:
                 # the MaxPool2d after conv1_2 / 2_2 / 3_4 / 4_4 is computed in the conv epilogue
                 fused_pool = ws.pool[s] if st.pool_idx is not None and ws.post[s] is not None else None

@@ -166,6 +166,11 @@ def relu_fwd(x: torch.Tensor, y: torch.Tensor) -> None:
     nat.call("stv_relu_fwd", nat.ptr(x), x.numel(), nat.ptr(y), _s(x))
 
 
+def relu_fwd_bits(x: torch.Tensor, y: torch.Tensor, bits: torch.Tensor | None) -> None:
+    """``y = tf32(relu(x))`` and its sign bits (``stv_relu_fwd_bits``)."""
+    nat.call("stv_relu_fwd_bits", nat.ptr(x), x.numel(), nat.ptr(y), nat.ptr(bits), _s(x))
+
+
 def relu_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, *, accumulate: bool) -> None:
     nat.call("stv_relu_bwd", nat.ptr(dy), nat.ptr(x), x.numel(), int(accumulate), nat.ptr(dx),
              _s(x))

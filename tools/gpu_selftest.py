@@ -51,6 +51,21 @@ def case_elementwise() -> bool:
     ok = True
     g = torch.Generator(device="cuda").manual_seed(0)
 
+    # relu + sign bits of a stored pre-activation (split ReLU of wide tapped layers)
+    for n_pix, c in [(37 * 53, 256), (64 * 64, 512), (9, 32)]:
+        xin = torch.randn(n_pix, c, device=dev, generator=g)
+        y = torch.full((n_pix, c), float("nan"), device=dev)
+        bits = torch.full((n_pix, c // 32), -1, device=dev, dtype=torch.int32)
+        ops.relu_fwd_bits(xin, y, bits)
+        want = xin.relu()
+        sh = torch.arange(32, device=dev, dtype=torch.int32)
+        unpacked = ((bits.unsqueeze(-1) >> sh) & 1).reshape(n_pix, c).bool()
+        ok &= report(f"relu_fwd_bits values {n_pix}x{c}", rel_l2(y, want), 3e-4)
+        ok &= report(f"relu_fwd_bits low bits zero {n_pix}x{c}",
+                     float((y.view(torch.int32) & 0x1FFF).abs().max()), 0)
+        ok &= report(f"relu_fwd_bits sign bits {n_pix}x{c}",
+                     0.0 if torch.equal(unpacked, y > 0) else 1.0, 0.0)
+
     # pack weights
     w = torch.randn(128, 64, 3, 3, device=dev, generator=g)
     wf, wd = ops.pack_conv_weights(w)
