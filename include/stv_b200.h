@@ -219,6 +219,43 @@ int stv_step_scores(const float* losses, int n_style, int n_content, float style
                     float* scores3, float* loss_ring, int* finite_ring, int capacity, int* counter,
                     void* stream);
 
+/* ---- general form of the tensor-core convolution -------------------------------------------- */
+/* Every stv_conv3x3_* entry point above is a fixed choice of the options of ONE kernel family;
+ * callers that combine them differently (the row-band sharded engine: haloed inputs, own-row
+ * outputs) fill this descriptor.  out = gate .* (alpha * conv(x, w) + bias) + add [+ style term];
+ * out_pre = out, out_post = relu(out); see the individual entry points for each field.  Zero /
+ * NULL = option off.  Returns 3 (nothing launched) when a fused style backward is requested for a
+ * shape whose tile family has no second accumulator. */
+typedef struct stv_conv_desc {
+  const float* x;          /* NHWC input [x_rows or H][W][C] */
+  const float* w_packed;   /* [taps][N][C] from stv_pack_conv_weights */
+  int H, W, C, N, taps;    /* output rows / cols, input / output channels, 9 or 1 */
+  int x_rows, x_row0;      /* haloed input: rows of x, and the row of x that lines up with output
+                              row 0 (0, 0 = x has H rows, zero padding at its edge) */
+  const float* bias;
+  const float* alpha;      /* device scalar */
+  const float* mask_src;   /* fp32 ReLU gate (x > 0) */
+  const float* add_src;
+  float* out_pre;
+  float* out_post;
+  int round_flags;         /* bit 0: store out_pre tf32-rounded, bit 1: out_post */
+  float* out_pool;
+  unsigned* out_bits;
+  unsigned* out_code;
+  const unsigned* mask_bits;
+  const unsigned* unpool_code;
+  int H2, W2;
+  const float* style_x;
+  const float* style_s;
+  const float* style_alpha;
+} stv_conv_desc;
+int stv_conv3x3_desc(const stv_conv_desc* d, void* stream);
+/* conv1_1 forward of a haloed image band: img NCHW [3][in_rows][W], output row 0 reads input rows
+ * in_row0 - 1 .. in_row0 + 1 (rows outside [0, in_rows) are zero padding). */
+int stv_conv3x3_first_fwd_band(const float* img_nchw, const float* w, const float* bias, int H,
+                               int W, int Cout, int in_rows, int in_row0, float* out_pre,
+                               float* out_post, unsigned* out_bits, int round_pre, void* stream);
+
 /* ---- row-band sharding over several GPUs (BASELINE configs[4]; no reference counterpart) ----- */
 /* Halo exchange of one haloed buffer [rows + 2][row_floats] (x planes) through PEER-MAPPED memory:
  * this GPU's kernels store its first / last own row into the lower halo of the rank above (`up`,

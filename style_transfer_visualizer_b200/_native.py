@@ -21,6 +21,21 @@ _l = ctypes.c_long
 _f = ctypes.c_float
 _sz = ctypes.c_size_t
 
+class ConvDesc(ctypes.Structure):
+    """``stv_conv_desc`` of include/stv_b200.h (field order and types must match)."""
+
+    _fields_ = [
+        ("x", _vp), ("w_packed", _vp),
+        ("H", _i), ("W", _i), ("C", _i), ("N", _i), ("taps", _i),
+        ("x_rows", _i), ("x_row0", _i),
+        ("bias", _vp), ("alpha", _vp), ("mask_src", _vp), ("add_src", _vp),
+        ("out_pre", _vp), ("out_post", _vp), ("round_flags", _i),
+        ("out_pool", _vp), ("out_bits", _vp), ("out_code", _vp),
+        ("mask_bits", _vp), ("unpool_code", _vp), ("H2", _i), ("W2", _i),
+        ("style_x", _vp), ("style_s", _vp), ("style_alpha", _vp),
+    ]
+
+
 # name -> argtypes; restype is int unless listed in _RESTYPES
 _SIGNATURES: dict[str, list] = {
     "stv_abi_version": [],
@@ -65,6 +80,8 @@ _SIGNATURES: dict[str, list] = {
     "stv_nchw_to_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "stv_nhwc_to_nchw": [_vp, _i, _i, _i, _vp, _vp],
     "stv_finite_flags": [_vp, _i, _vp, _vp],
+    "stv_conv3x3_desc": [ctypes.POINTER(ConvDesc), _vp],
+    "stv_conv3x3_first_fwd_band": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_halo_exchange": [_vp, _vp, _vp, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "stv_step_scores": [_vp, _i, _i, _f, _f, _vp, _vp, _vp, _i, _vp, _vp],
     "stv_conv_igemm2_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
@@ -72,6 +89,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_conv_set_tuning": [_i, _i, _i, _i],
     "stv_conv_ref": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
+
 _RESTYPES = {"stv_gram_workspace_bytes": _sz, "stv_lbfgs_workspace_floats": _sz}
 EXPORTED_SYMBOLS = ("stv_last_error", *_SIGNATURES)
 
@@ -142,6 +160,25 @@ def stream_for_call(device: torch.device) -> int:
     launched on while ``cuda:0`` is current (the reference accepts ``--device cuda:1``)."""
     _call_device[0] = device
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def call_status(name: str, *args) -> int:  # noqa: ANN002
+    """Like ``call`` but returns the status code 3 ("not fusable") instead of raising on it."""
+    lib = load()
+    _launches[0] += _KERNELS_PER_CALL.get(name, 1)
+    dev, _call_device[0] = _call_device[0], None
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
+    if rc not in (0, 3):
+        detail = lib.stv_last_error().decode("utf-8", "replace")
+        msg = f"{name} failed (status {rc}): {detail}"
+        raise NativeLibraryError(msg)
+    if rc == 3:
+        _launches[0] -= _KERNELS_PER_CALL.get(name, 1)
+    return rc
 
 
 def call(name: str, *args) -> None:  # noqa: ANN002

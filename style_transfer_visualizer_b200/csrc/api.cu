@@ -348,6 +348,27 @@ int stv_step_scores(const float* losses, int n_style, int n_content, float style
                             finite_ring, capacity, counter, S(stream));
 }
 
+int stv_conv3x3_desc(const stv_conv_desc* d, void* stream) {
+  STV_REQUIRE(d != nullptr, "stv_conv3x3_desc: null descriptor");
+  ConvArgs a;
+  a.x = d->x; a.w_packed = d->w_packed; a.H = d->H; a.W = d->W; a.C = d->C; a.N = d->N;
+  a.taps = d->taps; a.x_rows = d->x_rows; a.x_row0 = d->x_row0;
+  a.bias = d->bias; a.alpha = d->alpha; a.mask_src = d->mask_src; a.add_src = d->add_src;
+  a.out_pre = d->out_pre; a.out_post = d->out_post; a.round_flags = d->round_flags;
+  a.out_pool = d->out_pool; a.out_bits = d->out_bits; a.out_code = d->out_code;
+  a.mask_bits = d->mask_bits; a.unpool_code = d->unpool_code; a.H2 = d->H2; a.W2 = d->W2;
+  a.style_x = d->style_x; a.style_s = d->style_s; a.style_alpha = d->style_alpha;
+  return conv_igemm2_launch(a, S(stream));
+}
+int stv_conv3x3_first_fwd_band(const float* img_nchw, const float* w, const float* bias, int H,
+                               int W, int Cout, int in_rows, int in_row0, float* out_pre,
+                               float* out_post, unsigned* out_bits, int round_pre, void* stream) {
+  STV_REQUIRE(in_rows >= H + in_row0 - 1 && in_row0 >= 0,
+              "stv_conv3x3_first_fwd_band: %d input rows do not cover %d output rows", in_rows, H);
+  return conv_first_fwd_launch(img_nchw, w, bias, H, W, Cout, out_pre, out_post, out_bits,
+                               round_pre, S(stream), in_rows, in_row0);
+}
+
 int stv_halo_exchange(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
                       long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
                       unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, void* stream) {

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                       const float* __restrict__ bias, int H, int W, int groups_per_row,
                       int round_pre, float* __restrict__ out_pre, float* __restrict__ out_post,
-                      uint2* __restrict__ out_bits) {
+                      uint2* __restrict__ out_bits, int in_rows, int in_row0) {
   // let a following tensor-core conv (launched with programmatic stream serialization) run its
   // prologue under this kernel's tail; it still waits for our completion before touching data
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -37,7 +37,8 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
     reinterpret_cast<float*>(bs)[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
   __syncthreads();
 
-  const long hw = static_cast<long>(H) * W;
+  // the image may be a haloed band: in_rows rows per plane, row in_row0 = output row 0
+  const long hw = static_cast<long>(in_rows) * W;
   const int cq = threadIdx.x & 3;
   const long grp_raw = static_cast<long>(blockIdx.x) * 32 + (threadIdx.x >> 2);
   // groups past the end stay alive (the sign-bit shuffles below are warp-wide) but store nothing
@@ -51,8 +52,8 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
   for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      const bool rok = (yy >= 0) && (yy < H);
+      const int yy = y + ky - 1 + in_row0;
+      const bool rok = (yy >= 0) && (yy < in_rows);
       const float* row = img + ci * hw + static_cast<long>(yy) * W;
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
@@ -201,7 +202,7 @@ __global__ void conv_ref_kernel(const float* __restrict__ x, const float* __rest
 
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
                           int Cout, float* out_pre, float* out_post, unsigned* out_bits,
-                          int round_pre, cudaStream_t stream) {
+                          int round_pre, cudaStream_t stream, int in_rows, int in_row0) {
   STV_REQUIRE(Cout == kFirstCout, "conv_first_fwd: Cout must be %d (got %d)", kFirstCout, Cout);
   STV_REQUIRE(out_pre || out_post, "conv_first_fwd: no output buffer");
   STV_REQUIRE((reinterpret_cast<uintptr_t>(out_bits) & 7) == 0, "conv_first_fwd: out_bits alignment");
@@ -210,7 +211,8 @@ int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bi
   const unsigned blocks = static_cast<unsigned>((groups + 31) / 32);
   conv_first_fwd_kernel<<<blocks, 128, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
                                                     round_pre, out_pre, out_post,
-                                                    reinterpret_cast<uint2*>(out_bits));
+                                                    reinterpret_cast<uint2*>(out_bits),
+                                                    in_rows > 0 ? in_rows : H, in_row0);
   STV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

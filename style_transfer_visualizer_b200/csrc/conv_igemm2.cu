@@ -75,6 +75,8 @@ struct Conv2Params {
   // dF = gl * F * S of the tapped layer is a SECOND accumulator of the same tile, fed by style_kc
   // extra ring stages {F patch, S rows}; out = gate .* conv + gl * F S.  No separate 1x1 launch, no
   // round trip of the style gradient through memory.
+  int x_row0;                  // input row that lines up with output row 0 (1 when the input buffer
+                               // carries a halo row above the band: row-band sharding)
   int staged;                  // plain / un-pooling epilogue stores go through the shared-memory
                                // transpose (coalesced 128-byte lines); needs the staging tiles
   int style_kc;                // N / 32 slabs of the 1x1 contraction (0 = off)
@@ -280,10 +282,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             if (a_bytes) {
               if constexpr (PAIR)
                 tma_load_3d_pair(a_base + cur * p.a_stage_bytes, &tmap_x, a_full_c + 8 * cur, c << 5,
-                                 tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+                                 tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1) + p.x_row0);
               else
                 tma_load_3d(a_base + cur * p.a_stage_bytes, &tmap_x, a_full + 8 * cur, c << 5,
-                            tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1));
+                            tx0 + dxi - (ndx >> 1), ty0 - (ndy >> 1) + p.x_row0);
             }
             if (++as == AS) { as = 0; aph ^= 1; }
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
@@ -994,6 +996,9 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
               "conv_igemm2: pool codes are produced by the fused pool only");
   STV_REQUIRE(a.out_bits == nullptr || N != 16, "conv_igemm2: no sign bits on the N = 16 variant");
   STV_REQUIRE(!(a.mask_bits && a.mask_src), "conv_igemm2: give the ReLU gate as bits OR as fp32");
+  STV_REQUIRE(a.x_row0 >= 0 && (a.x_rows == 0 || a.x_rows >= H + a.x_row0),
+              "conv_igemm2: input rows %d / first row %d do not cover %d output rows", a.x_rows,
+              a.x_row0, H);
   if (a.unpool_code != nullptr) {
     STV_REQUIRE(a.out_pre != nullptr && a.out_post == nullptr && !a.mask_src && !a.add_src &&
                     !a.mask_bits && !a.out_pool && !a.bias && N != 16,
@@ -1037,6 +1042,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   p.mask_bits = a.mask_bits;
   p.unpool_code = a.unpool_code;
   p.H2 = a.H2; p.W2 = a.W2;
+  p.x_row0 = a.x_row0;
   p.style_kc = style ? N / 32 : 0;
   p.style_a_bytes = tc.th * tc.tw * 128;
   p.style_alpha = a.style_alpha;
@@ -1056,7 +1062,9 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
 
   CUtensorMap tx, twm;
   {
-    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)H};
+    // x_rows > H: the input buffer has halo rows around the band (the conv then reads real
+    // neighbour rows instead of the zero fill at the band edge)
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)(a.x_rows > 0 ? a.x_rows : H)};
     const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)W * C * 4};
     const uint32_t box[3] = {32, (uint32_t)tc.tw, (uint32_t)(tc.th + halo)};
     if (int rc = encode_tmap_f32(&tx, a.x, 3, dims, strides, box, kSwizzle128B)) return rc;

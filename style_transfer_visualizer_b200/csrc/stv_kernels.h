@@ -34,6 +34,9 @@ struct ConvArgs {
   const float* style_x = nullptr;
   const float* style_s = nullptr;
   const float* style_alpha = nullptr;
+  // row-band sharding: x is a haloed buffer of x_rows rows whose row x_row0 lines up with output
+  // row 0 (x_rows = 0: x has exactly H rows and the band edge is zero padding)
+  int x_rows = 0, x_row0 = 0;
   int force_n = 0, force_mh = 0, force_tw = 0;
 };
 // returned (nothing launched) when the tile family chosen for this shape has no second accumulator
@@ -57,7 +60,7 @@ int gram_from_r_launch(const float* r, int C, double n_total, const float* targe
 // conv_direct.cu --------------------------------------------------------------------------
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
                           int Cout, float* out_pre, float* out_post, unsigned* out_bits,
-                          int round_pre, cudaStream_t stream);
+                          int round_pre, cudaStream_t stream, int in_rows = 0, int in_row0 = 0);
 int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
                             float* dimg_nchw, cudaStream_t stream);
 int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,

@@ -126,6 +126,46 @@ def conv3x3_dgrad_unpool(dy: torch.Tensor, w_dgrad: torch.Tensor, pool_code: tor
              nat.ptr(pool_code), h2, w2, nat.ptr(dx), _s(dy))
 
 
+def conv3x3_desc(x: torch.Tensor, w_packed: torch.Tensor, *, rows: int, x_row0: int = 0,  # noqa: PLR0913
+                 taps: int = 9, bias: torch.Tensor | None = None,
+                 add_src: torch.Tensor | None = None, out_pre: torch.Tensor | None = None,
+                 out_post: torch.Tensor | None = None, round_flags: int = 0,
+                 out_pool: torch.Tensor | None = None, out_bits: torch.Tensor | None = None,
+                 out_code: torch.Tensor | None = None, mask_bits: torch.Tensor | None = None,
+                 unpool_code: torch.Tensor | None = None, unpool_hw: tuple[int, int] = (0, 0),
+                 style_x: torch.Tensor | None = None, style_s: torch.Tensor | None = None,
+                 style_alpha: torch.Tensor | None = None) -> bool:
+    """General form of the tensor-core conv (``stv_conv3x3_desc``): ``x`` may be a haloed buffer
+    ``[x_rows, W, C]`` whose row ``x_row0`` lines up with output row 0; the outputs cover ``rows``
+    rows.  Returns False (nothing launched) when a requested fused style backward is not available
+    for the shape."""
+    _chk(x, "x")
+    d = nat.ConvDesc()
+    d.x, d.w_packed = nat.ptr(x), nat.ptr(w_packed)
+    d.H, d.W, d.C, d.N, d.taps = rows, int(x.shape[1]), int(x.shape[2]), int(w_packed.shape[1]), taps
+    d.x_rows, d.x_row0 = int(x.shape[0]), x_row0
+    d.bias, d.add_src = nat.ptr(bias), nat.ptr(add_src)
+    d.out_pre, d.out_post, d.round_flags = nat.ptr(out_pre), nat.ptr(out_post), round_flags
+    d.out_pool, d.out_bits, d.out_code = nat.ptr(out_pool), nat.ptr(out_bits), nat.ptr(out_code)
+    d.mask_bits, d.unpool_code = nat.ptr(mask_bits), nat.ptr(unpool_code)
+    d.H2, d.W2 = unpool_hw
+    d.style_x, d.style_s, d.style_alpha = nat.ptr(style_x), nat.ptr(style_s), nat.ptr(style_alpha)
+    import ctypes
+
+    return nat.call_status("stv_conv3x3_desc", ctypes.byref(d), _s(x)) == 0
+
+
+def conv3x3_first_fwd_band(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,  # noqa: PLR0913
+                           out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
+                           rows: int, in_row0: int, round_pre: bool = False,
+                           out_bits: torch.Tensor | None = None) -> None:
+    """conv1_1 forward of a haloed NCHW image band ``[1, 3, in_rows, W]`` (``rows`` output rows)."""
+    _chk(img, "img")
+    nat.call("stv_conv3x3_first_fwd_band", nat.ptr(img), nat.ptr(w), nat.ptr(bias), rows,
+             int(img.shape[-1]), int(w.shape[0]), int(img.shape[-2]), in_row0, nat.ptr(out_pre),
+             nat.ptr(out_post), nat.ptr(out_bits), int(round_pre), _s(img))
+
+
 def conv3x3_first_dgrad(dy: torch.Tensor, w: torch.Tensor, dimg: torch.Tensor) -> None:
     _chk(dy, "dy")
     h, wd, cout = dy.shape

@@ -127,6 +127,8 @@ class _BandWorkspace:
     pool: list[torch.Tensor | None] = field(default_factory=list)
     d_y: list[torch.Tensor | None] = field(default_factory=list)
     d_pool: list[torch.Tensor | None] = field(default_factory=list)
+    bits: list[torch.Tensor | None] = field(default_factory=list)   # ReLU sign bits, own rows
+    code: list[torch.Tensor | None] = field(default_factory=list)   # pool routing bits, own rows
     gram_ws: list[torch.Tensor] = field(default_factory=list)
     s_mat: list[torch.Tensor] = field(default_factory=list)
     reduce_buf: torch.Tensor | None = None              # [sum C^2 + n_content] one all-reduce
@@ -256,11 +258,12 @@ class RowBandEngine:
                 else:
                     if tapped or st.relu_idx is None:
                         out.append(("pre", s, level, cols, st.cout, 1))
-                    if st.relu_idx is not None:
+                    if st.relu_idx is not None and st.pool_idx is None:
                         out.append(("post", s, level, cols, st.cout, 1))
                 if st.pool_idx is not None:
                     level, cols = level + 1, cols // 2
-                    out.append(("d_pool" if grads else "pool", s, level, cols, st.cout, 1))
+                    if not grads:   # the pooled gradient never reaches memory (un-pooling dgrad)
+                        out.append(("pool", s, level, cols, st.cout, 1))
             return out
 
         def allocate(specs, arena: _PeerArena | None) -> None:  # noqa: ANN001
@@ -312,8 +315,16 @@ class RowBandEngine:
                 ws.cols.append(cols)
                 if st.pool_idx is not None:
                     rows, cols = rows // 2, cols // 2
-            for name in ("pre", "post", "pool", "d_y", "d_pool"):
+            for name in ("pre", "post", "pool", "d_y", "d_pool", "bits", "code"):
                 setattr(ws, name, [None] * n)
+            for s, st in enumerate(self.stages):
+                if st.relu_idx is None or s + 1 >= n:
+                    continue
+                words = (ws.rows[s], ws.cols[s], st.cout // 32)   # own rows only: no halo needed
+                if st.pool_idx is not None:
+                    ws.code[s] = torch.zeros(*words, device=dev, dtype=torch.int32)
+                else:
+                    ws.bits[s] = torch.zeros(*words, device=dev, dtype=torch.int32)
             specs = haloed_specs(grads=False)
             ws.peer = arena_for(specs)
             allocate(specs, ws.peer)
@@ -361,21 +372,37 @@ class RowBandEngine:
 
     # ------------------------------------------------------------------ forward
     def _run_stack(self, x_band: torch.Tensor, ws: _BandWorkspace) -> None:
+        """Forward through the band.  Every conv READS the haloed buffer of its input (x_row0 = 1: the
+        halo rows supply the neighbours' pixels, zeros at the image edge) and WRITES own rows only,
+        with the same fused epilogues as the single-GPU engine: ReLU sign bits, 2x2 max pool +
+        routing bits (bands start on even rows, so pool windows never straddle a band), split ReLU
+        for the wide tapped layers."""
         ws.x_h[:, :, 1:-1, :].copy_(x_band)
         self._xchg_image(ws, ws.x_h)
         cur = None
         n = len(self.stages)
+        own = self._own
         for s, st in enumerate(self.stages):
+            rows = ws.rows[s]
+            rp = self._round_pre(st)
+            pre = own(ws.pre[s]) if ws.pre[s] is not None else None
+            post = own(ws.post[s]) if ws.post[s] is not None else None
             if s == 0:
-                ops.conv3x3_first_fwd(ws.x_h, st.weight, st.bias, ws.pre[0], ws.post[0],
-                                      round_pre=self._round_pre(st))
+                ops.conv3x3_first_fwd_band(ws.x_h, st.weight, st.bias, pre, post, rows=rows,
+                                           in_row0=1, round_pre=rp, out_bits=ws.bits[0])
+            elif st.pool_idx is not None:
+                ops.conv3x3_desc(cur, st.w_fwd, rows=rows, x_row0=1, bias=st.bias, out_pre=pre,
+                                 round_flags=2 | int(rp), out_pool=own(ws.pool[s]),
+                                 out_code=ws.code[s])
+            elif pre is not None and post is not None and st.cout >= 256:
+                ops.conv3x3_desc(cur, st.w_fwd, rows=rows, x_row0=1, bias=st.bias, out_pre=pre,
+                                 round_flags=2 | int(rp))
+                ops.relu_fwd_bits(pre, post, ws.bits[s])
             else:
-                ops.conv3x3_fwd(cur, st.w_fwd, st.bias, ws.pre[s], ws.post[s],
-                                round_pre=self._round_pre(st))
-            cur = ws.post[s] if ws.post[s] is not None else ws.pre[s]
-            if st.pool_idx is not None:
-                ops.maxpool2_fwd(self._own(ws.post[s]), self._own(ws.pool[s]))
-                cur = ws.pool[s]
+                ops.conv3x3_desc(cur, st.w_fwd, rows=rows, x_row0=1, bias=st.bias, out_pre=pre,
+                                 out_post=post, round_flags=2 | int(rp), out_bits=ws.bits[s])
+            cur = ws.pool[s] if st.pool_idx is not None else \
+                (ws.post[s] if ws.post[s] is not None else ws.pre[s])
             if s + 1 < n:
                 self._xchg(ws, cur, slot=1 + s)  # halos for the next 3x3 conv
 
@@ -452,39 +479,51 @@ class RowBandEngine:
         grad_w = grad_w.to(torch.float32).contiguous()
         ns = len(self.style_idx)
         n = len(self.stages)
+        own = self._own
         for s in range(n - 1, -1, -1):
             st = self.stages[s]
             down = self.stages[s + 1] if s + 1 < n else None
             d_y = ws.d_y[s]
-            acc = False
+            rows = ws.rows[s]
+            style_k = self.style_idx.index(st.conv_idx) if st.conv_idx in self.style_idx else None
+            content_k = self.content_idx.index(st.conv_idx) if st.conv_idx in self.content_idx \
+                else None
 
             def tap_grads(accumulate: bool) -> bool:
-                own = self._own(d_y)  # noqa: B023
-                if st.conv_idx in self.style_idx:  # noqa: B023
-                    k = self.style_idx.index(st.conv_idx)  # noqa: B023
-                    ops.style_bwd(self._own(ws.pre[s]), ws.s_mat[k], grad_w[k:k + 1], own,  # noqa: B023
-                                  accumulate=accumulate)
+                if style_k is not None:  # noqa: B023
+                    ops.style_bwd(own(ws.pre[s]), ws.s_mat[style_k], grad_w[style_k:style_k + 1],  # noqa: B023
+                                  own(d_y), accumulate=accumulate)  # noqa: B023
                     accumulate = True
-                if st.conv_idx in self.content_idx:  # noqa: B023
-                    k = self.content_idx.index(st.conv_idx)  # noqa: B023
-                    f = self._own(ws.pre[s])  # noqa: B023
+                if content_k is not None:  # noqa: B023
+                    f = own(ws.pre[s])  # noqa: B023
                     fh, fw = self._full_rows_at(s)  # noqa: B023
                     total = float(st.cout) * fh * fw  # noqa: B023
                     # kernel scales by 2 / n_local; rescale the weight to the global element count
-                    gw = grad_w[ns + k:ns + k + 1] * (float(f.numel()) / total)
-                    ops.content_loss_bwd(f, self.content_targets[k], gw, own, accumulate=accumulate)
+                    gw = grad_w[ns + content_k:ns + content_k + 1] * (float(f.numel()) / total)  # noqa: B023
+                    ops.content_loss_bwd(f, self.content_targets[content_k], gw, own(d_y),  # noqa: B023
+                                         accumulate=accumulate)
                     accumulate = True
                 return accumulate
 
             if st.pool_idx is not None:
-                ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, ws.d_pool[s])
-                ops.maxpool2_bwd(self._own(ws.d_pool[s]), self._own(ws.post[s]), self._own(d_y),
-                                 relu_mask=True)
+                # dgrad of the next conv at pooled resolution; its epilogue routes the gradient
+                # through the pool + ReLU backward straight into this stage's own rows
+                ops.conv3x3_desc(ws.d_y[s + 1], down.w_dgrad, rows=ws.rows[s + 1], x_row0=1,
+                                 out_pre=own(d_y), round_flags=1, unpool_code=ws.code[s],
+                                 unpool_hw=(rows, ws.cols[s]))
                 tap_grads(True)
             elif st.relu_idx is not None:
-                acc = tap_grads(False)
-                ops.conv3x3_dgrad(ws.d_y[s + 1], down.w_dgrad, d_y, relu_src=ws.post[s],
-                                  accumulate=acc)
+                fused = False
+                if style_k is not None and content_k is None and st.cout in (64, 128):
+                    fused = ops.conv3x3_desc(
+                        ws.d_y[s + 1], down.w_dgrad, rows=rows, x_row0=1, out_pre=own(d_y),
+                        round_flags=1, mask_bits=ws.bits[s], style_x=own(ws.pre[s]),
+                        style_s=ws.s_mat[style_k], style_alpha=grad_w[style_k:style_k + 1])
+                if not fused:
+                    acc = tap_grads(False)
+                    ops.conv3x3_desc(ws.d_y[s + 1], down.w_dgrad, rows=rows, x_row0=1,
+                                     out_pre=own(d_y), add_src=own(d_y) if acc else None,
+                                     round_flags=1, mask_bits=ws.bits[s])
             else:
                 tap_grads(False)
             self._xchg(ws, d_y, slot=s, grads=True)  # halos of the finished gradient feed the next dgrad
