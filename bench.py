@@ -263,6 +263,8 @@ def conv_flops(name: str, a: tuple) -> float | None:
         return 2.0 * 9 * a[3] * a[4] * a[5] * a[6]
     if name in CONV_DGRAD:                          # (dy, w, H, W, Cout, Cin, ...)
         return 2.0 * 9 * a[2] * a[3] * a[4] * a[5]
+    if name == "stv_conv3x3_dgrad_bits_style":      # dgrad + the fused 1x1 Gram backward of the layer
+        return 2.0 * 9 * a[2] * a[3] * a[4] * a[5] + 2.0 * a[2] * a[3] * a[5] * a[5]
     if name == "stv_conv3x3_first_dgrad_tc":        # (dy, w16, H, W, Cout, ...): 3 real channels
         return 2.0 * 9 * a[2] * a[3] * a[4] * 3
     if name == "stv_style_bwd":                     # (x, s, hw, C, ...)

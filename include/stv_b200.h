@@ -264,10 +264,14 @@ int stv_conv3x3_first_fwd_band(const float* img_nchw, const float* w, const floa
  * `flags_up` / `flags_down` are this process's mappings of the NEIGHBOURS' buffers (symmetric
  * memory); flags_*: [slots][4] words, zero-initialised; epoch / done: local [slots] words,
  * zero-initialised.  Every rank must issue the same sequence of (slot) exchanges.  On completion (in
- * stream order) the two halo rows of `mine` hold the neighbours' rows.  Graph-capturable. */
+ * stream order) the two halo rows of `mine` hold the neighbours' rows.  Graph-capturable.
+ * wait_ready != 0 adds a first round trip ("my buffer is final") before the push, needed only when
+ * some kernel of a rank writes into the halo rows of its own buffer (e.g. a conv run over band +
+ * halos); producers that store own rows only pass 0. */
 int stv_halo_exchange(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
                       long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
-                      unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, void* stream);
+                      unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, int wait_ready,
+                      void* stream);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 /* Explicit tile selection for the tensor-core conv: out = alpha*conv(x,w)+bias, optional relu gate /

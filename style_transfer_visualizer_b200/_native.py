@@ -82,7 +82,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_finite_flags": [_vp, _i, _vp, _vp],
     "stv_conv3x3_desc": [ctypes.POINTER(ConvDesc), _vp],
     "stv_conv3x3_first_fwd_band": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
-    "stv_halo_exchange": [_vp, _vp, _vp, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "stv_halo_exchange": [_vp, _vp, _vp, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "stv_step_scores": [_vp, _i, _i, _f, _f, _vp, _vp, _vp, _i, _vp, _vp],
     "stv_conv_igemm2_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                            _vp],

@@ -371,9 +371,11 @@ int stv_conv3x3_first_fwd_band(const float* img_nchw, const float* w, const floa
 
 int stv_halo_exchange(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
                       long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
-                      unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, void* stream) {
+                      unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, int wait_ready,
+                      void* stream) {
   return halo_exchange_launch(mine, up, down, rows, rows_up, rows_down, row_floats, planes,
-                              flags_mine, flags_up, flags_down, epoch, done, slot, S(stream));
+                              flags_mine, flags_up, flags_down, epoch, done, slot, wait_ready,
+                              S(stream));
 }
 
 int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int C, int N, int taps,

@@ -115,10 +115,14 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
   if (a.down) wait_flag(a.flags_mine + 4 * a.slot + 3, e, a.slot, 3);
 }
 
+__global__ void halo_epoch_kernel(unsigned* epoch, int slot) {
+  if (threadIdx.x == 0) epoch[slot] += 1u;
+}
+
 int halo_exchange_launch(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
                          long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
                          unsigned* flags_down, unsigned* epoch, unsigned* done, int slot,
-                         cudaStream_t stream) {
+                         int wait_ready, cudaStream_t stream) {
   STV_REQUIRE(mine && flags_mine && epoch && done, "halo_exchange: null buffer");
   STV_REQUIRE(rows >= 1 && row_floats > 0 && row_floats % 4 == 0,
               "halo_exchange: rows %d / row length %ld (must be a multiple of 4 floats)", rows,
@@ -135,7 +139,11 @@ int halo_exchange_launch(float* mine, float* up, float* down, int rows, int rows
   a.row_floats = row_floats; a.planes = planes;
   a.flags_mine = flags_mine; a.flags_up = flags_up; a.flags_down = flags_down;
   a.epoch = epoch; a.done = done; a.slot = slot;
-  halo_ready_kernel<<<1, 32, 0, stream>>>(a);
+  // wait_ready = 0: nothing on this rank or its neighbours writes the halo rows of this buffer
+  // except the exchange itself (every producer stores own rows only), so the "my buffer is final"
+  // round trip is skipped and only the epoch advances
+  if (wait_ready) halo_ready_kernel<<<1, 32, 0, stream>>>(a);
+  else halo_epoch_kernel<<<1, 32, 0, stream>>>(epoch, slot);
   STV_CHECK_CUDA(cudaGetLastError());
   const long items = 2L * planes * (row_floats / 4);
   long blocks = (items + 255) / 256;

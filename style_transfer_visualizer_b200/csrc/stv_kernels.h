@@ -113,6 +113,6 @@ int step_scores_launch(const float* losses, int n_style, int n_content, float st
 int halo_exchange_launch(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
                          long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
                          unsigned* flags_down, unsigned* epoch, unsigned* done, int slot,
-                         cudaStream_t stream);
+                         int wait_ready, cudaStream_t stream);
 
 }  // namespace stv

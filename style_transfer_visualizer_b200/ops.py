@@ -358,13 +358,14 @@ def finite_flags(vals: torch.Tensor, flags: torch.Tensor) -> None:
 def halo_exchange(mine: torch.Tensor, *, up_ptr: int | None, down_ptr: int | None,  # noqa: PLR0913
                   rows: int, rows_up: int, rows_down: int, row_floats: int, planes: int,
                   flags_mine: torch.Tensor, flags_up_ptr: int | None, flags_down_ptr: int | None,
-                  epoch: torch.Tensor, done: torch.Tensor, slot: int) -> None:
+                  epoch: torch.Tensor, done: torch.Tensor, slot: int,
+                  wait_ready: bool = True) -> None:
     """Push this rank's boundary rows into the neighbours' halo rows through peer-mapped memory and
     wait for theirs (``stv_halo_exchange``).  ``*_ptr`` are this process's mappings of the
     neighbours' buffers (None at the image boundary)."""
     nat.call("stv_halo_exchange", nat.ptr(mine), up_ptr, down_ptr, rows, rows_up, rows_down,
              row_floats, planes, nat.ptr(flags_mine), flags_up_ptr, flags_down_ptr, nat.ptr(epoch),
-             nat.ptr(done), slot, _s(mine))
+             nat.ptr(done), slot, int(wait_ready), _s(mine))
 
 
 def step_scores(losses: torch.Tensor, n_style: int, n_content: int, style_w: float,  # noqa: PLR0913

@@ -202,7 +202,8 @@ class RowBandEngine:
             row_floats=row_floats, planes=planes, flags_mine=pa.flags,
             flags_up_ptr=None if up is None else pa.flag_base[up],
             flags_down_ptr=None if down is None else pa.flag_base[down],
-            epoch=pa.epoch, done=pa.done, slot=slot)
+            epoch=pa.epoch, done=pa.done, slot=slot,
+            wait_ready=False)  # every producer of this engine stores own rows only
 
     def _xchg_image(self, ws: _BandWorkspace, img_h: torch.Tensor) -> None:
         """Halo rows of the NCHW image band: the 3 planes' rows are packed into one message."""

@@ -457,3 +457,73 @@ def test_closure_reads_no_scalars_between_flushes(monkeypatch) -> None:  # noqa:
     monkeypatch.undo()
     # one flush at step 5 (three scalars) -- nothing at steps 1-4 and 6-9
     assert calls["n"] <= 3
+
+
+# --------------------------------------------------------------------------- round-2 host logic
+def test_accumulator_adopts_rows_written_by_the_step_graph() -> None:
+    """``adopt_device_rows``: the captured step graph writes row ``k % capacity`` itself
+    (``stv_step_scores``); ``accumulate`` then only keeps the books, ``export_history`` returns the
+    retained window oldest-first and the logged scalars come from the row, not from the tensors."""
+    from style_transfer_visualizer_b200.loss_accumulator import LossAccumulator
+
+    cap = 4
+    acc = LossAccumulator(log_every=2, history_capacity=cap, track_history=True,
+                          device=torch.device("cpu"), dtype=torch.float32)
+    rows = torch.zeros(cap, 3)
+    acc.adopt_device_rows(rows)
+    junk = torch.tensor(-1.0)
+    logged = []
+    for step in range(1, 7):                        # the "graph" writes the row, then accumulate()
+        rows[(step - 1) % cap] = torch.tensor([step, 10.0 * step, 100.0 * step])
+        out = acc.accumulate(step, junk, junk, junk)
+        if out is not None:
+            logged.append((out.step, out.style_loss, out.content_loss, out.total_loss))
+    assert logged == [(2, 2.0, 20.0, 200.0), (4, 4.0, 40.0, 400.0), (6, 6.0, 60.0, 600.0)]
+    hist = acc.export_history()
+    assert hist["style_loss"] == [3.0, 4.0, 5.0, 6.0]      # the last `cap` steps, oldest first
+    assert hist["total_loss"] == [300.0, 400.0, 500.0, 600.0]
+    assert acc.history_truncated
+    with pytest.raises(RuntimeError, match="must precede"):
+        acc.adopt_device_rows(rows)
+    with pytest.raises(ValueError, match="shape"):
+        LossAccumulator(log_every=1, history_capacity=cap, track_history=True,
+                        device=torch.device("cpu"), dtype=torch.float32
+                        ).adopt_device_rows(torch.zeros(cap + 1, 3))
+
+
+def test_bench_accounting_helpers() -> None:
+    """bench.py: every tensor-core conv entry point is counted with its algorithmic FLOPs, and the
+    TF32 roofline denominator follows the clock / power regime sampled during the timed blocks."""
+    import bench
+
+    h, w, cin, cout = 8, 16, 64, 128
+    fwd = 2.0 * 9 * h * w * cin * cout
+    for name in bench.CONV_FWD:
+        assert bench.conv_flops(name, (0, 0, 0, h, w, cin, cout)) == fwd
+    for name in bench.CONV_DGRAD:
+        assert bench.conv_flops(name, (0, 0, h, w, cout, cin)) == fwd
+    assert bench.conv_flops("stv_conv3x3_first_dgrad_tc", (0, 0, h, w, 64)) == 2.0 * 9 * h * w * 64 * 3
+    assert bench.conv_flops("stv_style_bwd", (0, 0, 100, 64)) == 2.0 * 100 * 64 * 64
+    assert bench.conv_flops("stv_adam_step", ()) is None
+    # every conv entry point the native layer exports is covered by the accounting
+    conv_like = {n for n in nat.EXPORTED_SYMBOLS
+                 if n.startswith(("stv_conv3x3_fwd", "stv_conv3x3_dgrad"))}
+    assert conv_like <= set(bench.CONV_FWD) | set(bench.CONV_DGRAD) | {"stv_conv3x3_dgrad_bits_style"}
+    assert bench.conv_flops("stv_conv3x3_dgrad_bits_style", (0, 0, h, w, cout, cin)) == \
+        fwd + 2.0 * h * w * cin * cin
+    peaks = {"bf16_burst": 1646.0, "bf16_sustained": 1399.4, "hbm_gbs": 6546.2, "source": "x"}
+    full = {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []}
+    capped = {"sm_mhz": 1740.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"]}
+    assert bench.tensor_peak(peaks, full)[0] == 823.0
+    assert bench.tensor_peak(peaks, capped)[0] == 699.7
+    assert bench.tensor_peak(peaks, None)[0] == 823.0
+
+
+def test_band_rows_and_arena_layout() -> None:
+    from style_transfer_visualizer_b200.sharded import plan_bands, rows_at
+
+    assert [rows_at(272, k) for k in range(5)] == [272, 136, 68, 34, 17]
+    assert rows_at(135, 1) == 67 and rows_at(135, 2) == 33      # floor mode, level by level
+    bands = plan_bands(2160, 8)
+    assert [b - a for a, b in bands] == [272] * 7 + [256]
+    assert all(a % 16 == 0 for a, _ in bands) and bands[-1][1] == 2160

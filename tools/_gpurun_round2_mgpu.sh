@@ -10,7 +10,7 @@ for mode in peer nccl; do
   python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/r2_bench_4k_${N}gpu_${mode}.json"))
+    d=[json.loads(l) for l in open("gpurun_out/r2_bench_4k_${N}gpu_${mode}.json") if l.startswith("{")][-1]
     print("4k x$N $mode:", round(d["value"],2), "steps/s", d["config"]["halo_exchange"], "launches/step", d["gpu_launches_per_step"], "parity", d["parity_vs_golden"])
 except Exception as e:
     print("ERR", e); print(open("gpurun_out/r2_bench_4k_${N}gpu_${mode}.err").read()[-2000:])
@@ -21,7 +21,7 @@ timeout 900 $TR --master-port 29613 bench.py --gpus $N --steps 20 --warmup 5 > g
 python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/r2_bench_default_${N}gpu.json"))
+    d=[json.loads(l) for l in open("gpurun_out/r2_bench_default_${N}gpu.json") if l.startswith("{")][-1]
     print("default x$N:", round(d["value"],1), "e2e", round(d["e2e"]["value"],1)); print("  sharded_4k:", {k:v for k,v in d["workloads"]["sharded_4k"].items() if k in ("value","efficiency_vs_n1","n1_value_unsharded","parity_vs_golden","halo_exchange")})
 except Exception as e:
     print("ERR", e); print(open("gpurun_out/r2_bench_default_${N}gpu.err").read()[-2000:])
