@@ -15,10 +15,12 @@ namespace stv {
 
 constexpr int kFirstCout = 64;
 
-// One thread = 4 consecutive pixels of a row x 16 output channels (quads cq, cq+4, cq+8, cq+12 with
-// cq = lane % 4).  Each weight quad read from shared memory (one LDS.128) feeds 16 FMAs, so the
-// kernel is FMA- rather than LDS-bound, and the four cq lanes of a pixel write 64 contiguous bytes
-// (full 32-byte sectors) per store instruction.
+// One thread = kFirstPx consecutive pixels of a row x 16 output channels (quads cq, cq+4, cq+8,
+// cq+12 with cq = lane % 4).  Each weight quad read from shared memory (one LDS.128) feeds
+// 4 * kFirstPx FMAs -- with 8 pixels the kernel is FMA- rather than LDS-bound (with 4 pixels the two
+// pipes were balanced at ~50 % each and the layer ran at 3.0 TB/s of stores) -- and the four cq
+// lanes of a pixel write 64 contiguous bytes (full 32-byte sectors) per store instruction.
+constexpr int kFirstPx = 8;
 __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                       const float* __restrict__ bias, int H, int W, int groups_per_row,
@@ -45,9 +47,9 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
   const bool active = grp_raw < static_cast<long>(groups_per_row) * H;
   const long grp = active ? grp_raw : 0;
   const int y = static_cast<int>(grp / groups_per_row);
-  const int x0 = static_cast<int>(grp % groups_per_row) * 4;
+  const int x0 = static_cast<int>(grp % groups_per_row) * kFirstPx;
 
-  float in[3][3][6];  // [channel][row][x0-1 .. x0+4]
+  float in[3][3][kFirstPx + 2];  // [channel][row][x0-1 .. x0+kFirstPx]
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -56,7 +58,7 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
       const bool rok = (yy >= 0) && (yy < in_rows);
       const float* row = img + ci * hw + static_cast<long>(yy) * W;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
+      for (int j = 0; j < kFirstPx + 2; ++j) {
         const int xx = x0 + j - 1;
         in[ci][ky][j] = (rok && xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
       }
@@ -64,14 +66,16 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
 
   const long pix0 = static_cast<long>(y) * W + x0;
   // sign bits of the post-ReLU values (the ReLU gate of conv1_2's dgrad): word 0 = channels 0..31,
-  // word 1 = channels 32..63 of each of this thread's four pixels
-  uint32_t sb0[4] = {0u, 0u, 0u, 0u}, sb1[4] = {0u, 0u, 0u, 0u};
+  // word 1 = channels 32..63 of each of this thread's pixels
+  uint32_t sb0[kFirstPx], sb1[kFirstPx];
+#pragma unroll
+  for (int px = 0; px < kFirstPx; ++px) { sb0[px] = 0u; sb1[px] = 0u; }
 #pragma unroll 1
   for (int i = 0; i < kFirstCout / 16; ++i) {
     const int c4 = i * 4 + cq;
-    float4 acc[4];
+    float4 acc[kFirstPx];
 #pragma unroll
-    for (int px = 0; px < 4; ++px) acc[px] = bs[c4];
+    for (int px = 0; px < kFirstPx; ++px) acc[px] = bs[c4];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -80,7 +84,7 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
         for (int kx = 0; kx < 3; ++kx) {
           const float4 wk = ws[ci * 9 + ky * 3 + kx][c4];
 #pragma unroll
-          for (int px = 0; px < 4; ++px) {
+          for (int px = 0; px < kFirstPx; ++px) {
             const float v = in[ci][ky][px + kx];
             acc[px].x = fmaf(v, wk.x, acc[px].x);
             acc[px].y = fmaf(v, wk.y, acc[px].y);
@@ -89,7 +93,7 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
           }
         }
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
+    for (int px = 0; px < kFirstPx; ++px) {
       if (active && x0 + px < W) {
         const long o = (pix0 + px) * (kFirstCout / 4) + c4;
         if (out_pre) {
@@ -116,13 +120,14 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
   }
   if (out_bits) {  // warp-uniform
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
+    for (int px = 0; px < kFirstPx; ++px) {
       // OR over the four channel-quad lanes of the pixel group (adjacent lanes: cq = lane % 4)
       sb0[px] |= __shfl_xor_sync(0xffffffffu, sb0[px], 1);
       sb0[px] |= __shfl_xor_sync(0xffffffffu, sb0[px], 2);
       sb1[px] |= __shfl_xor_sync(0xffffffffu, sb1[px], 1);
       sb1[px] |= __shfl_xor_sync(0xffffffffu, sb1[px], 2);
-      if (cq == px && active && x0 + px < W) out_bits[pix0 + px] = make_uint2(sb0[px], sb1[px]);
+      if ((px & 3) == cq && active && x0 + px < W)
+        out_bits[pix0 + px] = make_uint2(sb0[px], sb1[px]);
     }
   }
 }
@@ -206,7 +211,7 @@ int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bi
   STV_REQUIRE(Cout == kFirstCout, "conv_first_fwd: Cout must be %d (got %d)", kFirstCout, Cout);
   STV_REQUIRE(out_pre || out_post, "conv_first_fwd: no output buffer");
   STV_REQUIRE((reinterpret_cast<uintptr_t>(out_bits) & 7) == 0, "conv_first_fwd: out_bits alignment");
-  const int groups_per_row = (W + 3) / 4;
+  const int groups_per_row = (W + kFirstPx - 1) / kFirstPx;
   const long groups = static_cast<long>(groups_per_row) * H;
   const unsigned blocks = static_cast<unsigned>((groups + 31) / 32);
   conv_first_fwd_kernel<<<blocks, 128, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
