@@ -287,6 +287,10 @@ int stv_conv_igemm2_ex(const float* x, const float* w_packed, int H, int W, int 
  * table (default).  a_stages / b_stages (operand ring depths) and taps_per_stage (1 or 3 weight taps
  * per ring stage): 0 = built-in defaults. */
 int stv_conv_set_tuning(int pair_mode, int a_stages, int b_stages, int taps_per_stage);
+/* Epilogue store policy of the plain / un-pooling epilogues for the calling host thread: -1 = the
+ * measured rule (coalesced shared-memory-transposed stores where a value is stored more than once or
+ * the epilogue is the bottleneck), 0 = always direct, 1 = coalesced wherever the tile allows. */
+int stv_conv_set_epilogue(int staged_mode);
 /* Naive CUDA-core NHWC conv, same packed weights; on-device cross-check only. */
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream);

@@ -398,6 +398,11 @@ int stv_conv_set_tuning(int pair_mode, int a_stages, int b_stages, int taps_per_
   conv_set_tuning(pair_mode, a_stages, b_stages, taps_per_stage);
   return 0;
 }
+int stv_conv_set_epilogue(int staged_mode) {
+  STV_REQUIRE(staged_mode >= -1 && staged_mode <= 1, "stv_conv_set_epilogue: mode must be -1, 0 or 1");
+  conv_set_epilogue(staged_mode);
+  return 0;
+}
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream) {
   return conv_ref_launch(x, w_packed, bias, H, W, C, N, taps, relu, out, S(stream));

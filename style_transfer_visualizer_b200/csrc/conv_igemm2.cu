@@ -830,8 +830,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 struct ConvTuning {
   int pair_mode = -1;                      // -1: rule table, 0: never, 1: whenever the shape allows
   int a_stages = 0, b_stages = 0, tps = 0;  // ring depth / taps-per-stage overrides (0 = defaults)
+  int staged = -1;                          // epilogue stores: -1 rule, 0 direct, 1 coalesced
 };
 static thread_local ConvTuning g_tuning;
+void conv_set_epilogue(int staged_mode) { g_tuning.staged = staged_mode; }
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
   g_tuning.pair_mode = pair_mode;
   g_tuning.a_stages = a_stages;
@@ -1106,7 +1108,8 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   // costs 15-35 % on single-output forward layers, which therefore keep the direct stores.
   const bool staged_pays = a.unpool_code != nullptr || (a.out_pre != nullptr && a.out_post != nullptr) ||
                            (a.out_pre != nullptr && a.out_post == nullptr && a.out_pool == nullptr);
-  if (!staging_needed && staged_pays && N != 16 && tc.block_n <= 128) {
+  const bool want_staged = g_tuning.staged < 0 ? staged_pays : g_tuning.staged == 1;
+  if (!staging_needed && want_staged && N != 16 && tc.block_n <= 128) {
     auto depth_for = [&](bool stg) {
       int depth = p.uni ? ((tc.block_n == 64 && tc.mh == 1) ? 2 : 4) : 4;
       if (p.uni && env_as > 0) depth = env_as;

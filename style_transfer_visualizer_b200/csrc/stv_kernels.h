@@ -47,6 +47,8 @@ int conv_igemm2_launch(const ConvArgs& args, cudaStream_t stream);
 // single-CTA tiles only; 1: CTA pairs (cta_group::2) wherever legal.  a_stages / b_stages / tps > 0
 // override the ring depths and weight taps per stage.
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps);
+// epilogue store policy of the calling thread: -1 measured rule, 0 direct, 1 coalesced where possible
+void conv_set_epilogue(int staged_mode);
 
 // gram.cu ---------------------------------------------------------------------------------
 size_t gram_workspace_bytes(long hw, int C);

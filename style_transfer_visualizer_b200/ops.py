@@ -410,6 +410,11 @@ def conv_set_tuning(pair_mode: int = -1, a_stages: int = 0, b_stages: int = 0, t
     nat.call("stv_conv_set_tuning", int(pair_mode), int(a_stages), int(b_stages), int(tps))
 
 
+def conv_set_epilogue(staged_mode: int = -1) -> None:
+    """-1: measured rule, 0: direct stores, 1: coalesced (staged) stores wherever the tile allows."""
+    nat.call("stv_conv_set_epilogue", int(staged_mode))
+
+
 def conv_set_pair_mode(mode: int) -> None:
     """-1: built-in rule table, 0: single-CTA conv tiles only, 1: CTA pairs wherever legal."""
     conv_set_tuning(mode)

@@ -1,5 +1,6 @@
 # final single-GPU validation + evidence of the round
 mkdir -p gpurun_out
+timeout 600 python tools/epilogue_ab_512.py > gpurun_out/r2_epilogue_ab_512.log 2>&1; cat gpurun_out/r2_epilogue_ab_512.log | tail -60
 timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu_final.log 2>&1; tail -6 gpurun_out/r2_pytest_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
 python bench.py > gpurun_out/r2_bench_default_final.json 2> gpurun_out/r2_bench_default_final.err; echo "bench rc=$?"
