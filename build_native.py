@@ -24,11 +24,16 @@ def needs_rebuild() -> bool:
     return newest > OUT.stat().st_mtime
 
 
-def build(*, force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_rebuild():
+def build(*, force: bool = False, verbose: bool = False, experiments: bool = False) -> Path:
+    """``experiments=True`` compiles the bottleneck-experiment switches in (``-DSTV_EXPERIMENTS``:
+    the conv kernel then honours the STV_CONV_DEBUG environment variable and produces garbage
+    when it is set) -- for tools/conv_bottleneck.py and tools/conv_chain_latency.py only; the
+    product build never reads the environment."""
+    if not force and not experiments and not needs_rebuild():
         return OUT
     OUT.parent.mkdir(parents=True, exist_ok=True)
-    cmd = ["nvcc", *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT),
+    cmd = ["nvcc", *FLAGS, *(["-DSTV_EXPERIMENTS"] if experiments else []),
+           *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT),
            *[str(CSRC / s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True, check=False)
     if verbose or proc.returncode != 0:
@@ -40,4 +45,5 @@ def build(*, force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                experiments="--experiments" in sys.argv))

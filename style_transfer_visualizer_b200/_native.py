@@ -141,7 +141,7 @@ def stream_ptr(device: torch.device | None = None) -> int:
 
 # kernels enqueued per entry point (everything else launches exactly one)
 _KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_gram_partial_r": 2, "stv_gram_from_r": 2, "stv_content_loss_fwd": 2, "stv_dot": 2,
-                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_halo_exchange": 2, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0, "stv_conv_set_epilogue": 0, "stv_conv_set_tuning": 0,
+                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_halo_exchange": 1, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0, "stv_conv_set_epilogue": 0, "stv_conv_set_tuning": 0,
                      "stv_device_check": 0}
 _launches = [0]
 

@@ -69,8 +69,12 @@ __global__ void halo_ready_kernel(const HaloArgs a) {
   if (a.down) wait_flag(a.flags_mine + 4 * a.slot + 1, e, a.slot, 1);
 }
 
-__global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
-  const unsigned e = a.epoch[a.slot];
+// own_epoch != 0: no halo_ready kernel ran before this one; every block derives the epoch of this
+// exchange from the last completed one and the last block publishes it (all blocks have read
+// epoch[slot] before they add to `done`, and the previous exchange of the slot is complete in
+// stream order)
+__global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a, const int own_epoch) {
+  const unsigned e = a.epoch[a.slot] + (own_epoch ? 1u : 0u);
   const long row4 = a.row_floats >> 2;
   const long per_plane_mine = static_cast<long>(a.rows + 2) * a.row_floats;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -108,15 +112,12 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
   const unsigned prev = atomicAdd(a.done + a.slot, 1u);
   if (prev != gridDim.x - 1) return;
   a.done[a.slot] = 0;
+  if (own_epoch) a.epoch[a.slot] = e;
   __threadfence_system();  // all blocks' peer stores are visible before the flags below
   if (a.up) st_release_sys(a.flags_up + 4 * a.slot + 3, e);
   if (a.down) st_release_sys(a.flags_down + 4 * a.slot + 2, e);
   if (a.up) wait_flag(a.flags_mine + 4 * a.slot + 2, e, a.slot, 2);
   if (a.down) wait_flag(a.flags_mine + 4 * a.slot + 3, e, a.slot, 3);
-}
-
-__global__ void halo_epoch_kernel(unsigned* epoch, int slot) {
-  if (threadIdx.x == 0) epoch[slot] += 1u;
 }
 
 int halo_exchange_launch(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
@@ -141,15 +142,16 @@ int halo_exchange_launch(float* mine, float* up, float* down, int rows, int rows
   a.epoch = epoch; a.done = done; a.slot = slot;
   // wait_ready = 0: nothing on this rank or its neighbours writes the halo rows of this buffer
   // except the exchange itself (every producer stores own rows only), so the "my buffer is final"
-  // round trip is skipped and only the epoch advances
-  if (wait_ready) halo_ready_kernel<<<1, 32, 0, stream>>>(a);
-  else halo_epoch_kernel<<<1, 32, 0, stream>>>(epoch, slot);
-  STV_CHECK_CUDA(cudaGetLastError());
+  // round trip is skipped: ONE launch per exchange, the push kernel advances the epoch itself
+  if (wait_ready) {
+    halo_ready_kernel<<<1, 32, 0, stream>>>(a);
+    STV_CHECK_CUDA(cudaGetLastError());
+  }
   const long items = 2L * planes * (row_floats / 4);
   long blocks = (items + 255) / 256;
   if (blocks > 64) blocks = 64;
   if (blocks < 1) blocks = 1;
-  halo_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a);
+  halo_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, wait_ready ? 0 : 1);
   STV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

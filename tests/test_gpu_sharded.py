@@ -29,3 +29,23 @@ def test_row_band_sharding_matches_single_gpu() -> None:
     lines = [ln for ln in proc.stdout.splitlines() if ln.startswith(("PASS", "FAIL"))]
     assert proc.returncode == 0 and lines and all(ln.startswith("PASS") for ln in lines), \
         proc.stdout[-3000:] + proc.stderr[-3000:]
+
+
+def test_model_on_second_gpu_while_first_is_current() -> None:
+    """The reference accepts ``--device cuda:1``.  The native launches use the CURRENT device's
+    context (kernel attributes, SM count, stream): every call must switch to the tensors' device
+    (``_native.call``) and the per-device caches of the library must be filled for that device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from tests import _cases as cases
+    from tests import _gpu_run
+
+    cfg, gold = cases.load_golden("adam_content_64")
+    torch.cuda.set_device(0)
+    res = _gpu_run.run_case(cfg, torch.device("cuda:1"), use_cuda_graph=True)
+    m = _gpu_run.compare(cfg, gold, res)
+    assert torch.cuda.current_device() == 0
+    assert m["grad_rel_l2"] <= 0.021 and m["layer_style_rel_max"] <= 0.0011
+    assert m["total_rel_max"] <= 3e-4

@@ -1,5 +1,8 @@
 """Bottleneck experiments on single conv layers: STV_CONV_DEBUG bits disable weight loads (1),
-activation loads (2), epilogue stores (4), MMAs (8); results are garbage, only the time matters."""
+activation loads (2), epilogue stores (4), MMAs (8); results are garbage, only the time matters.
+Needs the experiments build of the library: `python build_native.py --force --experiments` (the
+product build does not read STV_CONV_DEBUG); rebuild without the flag afterwards.
+"""
 import os, sys, subprocess
 code = r'''
 import sys, os, torch

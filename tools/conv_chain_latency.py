@@ -1,5 +1,8 @@
 """Handoff-chain experiment: one 64x64 512->512 conv under STV_CONV_DEBUG modes (15 = control skeleton
-only, 7 = MMAs only, 3 = no loads, 0 = full) for several ring configurations (profiles/r1_conv_chain_latency.log)."""
+only, 7 = MMAs only, 3 = no loads, 0 = full) for several ring configurations (profiles/r1_conv_chain_latency.log).
+Needs the experiments build of the library: `python build_native.py --force --experiments` (the
+product build does not read STV_CONV_DEBUG); rebuild without the flag afterwards.
+"""
 import os, sys, subprocess
 code = r'''
 import sys, os, torch

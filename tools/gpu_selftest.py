@@ -578,7 +578,7 @@ def case_halo() -> bool:
         flags = [torch.zeros(64 * 4, device=dev, dtype=torch.int32) for _ in range(n)]
         epoch = [torch.zeros(64, device=dev, dtype=torch.int32) for _ in range(n)]
         done = [torch.zeros(64, device=dev, dtype=torch.int32) for _ in range(n)]
-        for it in range(1, 4):      # three epochs
+        for it in range(1, 5):      # four epochs; the last two without the "ready" round trip
             for r in range(n):
                 bufs = [torch.randn(planes, rows + 2, row_floats, device=dev) for rows in rows_of]
                 before = [b.clone() for b in bufs]
@@ -592,7 +592,7 @@ def case_halo() -> bool:
                     planes=planes, flags_mine=flags[r],
                     flags_up_ptr=flags[r - 1].data_ptr() if r > 0 else None,
                     flags_down_ptr=flags[r + 1].data_ptr() if r < n - 1 else None,
-                    epoch=epoch[r], done=done[r], slot=slot)
+                    epoch=epoch[r], done=done[r], slot=slot, wait_ready=it <= 2)
                 torch.cuda.synchronize()
                 want = [b.clone() for b in before]
                 if r > 0:
@@ -605,12 +605,12 @@ def case_halo() -> bool:
                     want[r][:, rows_of[r] + 1] = 0.0
                 same = all(torch.equal(bufs[k], want[k]) for k in range(n))
                 same = same and int(epoch[r][slot]) == it and int(done[r][slot]) == 0
-                if r > 0:       # A / B "from below" raised at the rank above
-                    same = same and flags[r - 1][4 * slot + 1].item() == it \
-                        and flags[r - 1][4 * slot + 3].item() == it
-                if r < n - 1:   # A / B "from above" raised at the rank below
-                    same = same and flags[r + 1][4 * slot + 0].item() == it \
-                        and flags[r + 1][4 * slot + 2].item() == it
+                if r > 0:       # B (and A when requested) "from below" raised at the rank above
+                    same = same and flags[r - 1][4 * slot + 3].item() == it \
+                        and (it > 2 or flags[r - 1][4 * slot + 1].item() == it)
+                if r < n - 1:   # B (and A) "from above" raised at the rank below
+                    same = same and flags[r + 1][4 * slot + 2].item() == it \
+                        and (it > 2 or flags[r + 1][4 * slot + 0].item() == it)
                 ok &= report(f"halo push planes={planes} rows={rows_of} row={row_floats} rank={r} "
                              f"epoch={it}", 0.0 if same else 1.0, 0.0)
     return ok
