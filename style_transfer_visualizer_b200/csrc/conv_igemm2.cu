@@ -1119,7 +1119,8 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
         --depth;
       return depth;
     };
-    if (p.uni && depth_for(true) == depth_for(false) &&
+    // (the explicit policy override may trade a ring stage for the staging tiles: experiments)
+    if (p.uni && (depth_for(true) == depth_for(false) || g_tuning.staged == 1) &&
         conv2_smem_bytes(p.a_stage_bytes, depth_for(true), depth_for(true), p.tps, b_rows, N,
                          tc.block_n, tc.mh, true) <= 227 * 1024) {
       staging = true;

@@ -52,6 +52,22 @@ def main() -> None:
             rule = timed(fn, reps=20)
             print(f"   {name:<22s} direct {out[0]:7.1f} us  staged {out[1]:7.1f} us  rule {rule:7.1f} us "
                   f"({gf / rule * 1e3:6.1f} TF/s)", flush=True)
+        # forced tile families for the wide layers: is a narrower, coalesced-store tile better than
+        # the 256-wide direct-store one when every CTA has a single tile?
+        if cout >= 256:
+            for (bn, mh, pair) in [(256, 1, 1), (128, 2, 1), (128, 1, 0), (128, 1, 1)]:
+                for mode in (0, 1):
+                    ops.conv_set_tuning(pair)
+                    ops.conv_set_epilogue(mode)
+                    try:
+                        us = timed(lambda: ops.conv_igemm2_ex(x, wf, taps=9, bias=b, out_pre=pre,  # noqa: B023
+                                                              block_n=bn, m_halves=mh), reps=20)  # noqa: B023
+                        print(f"   forced bn{bn} mh{mh} pair{pair} staged{mode} (out_pre only) "
+                              f"{us:7.1f} us ({gf / us * 1e3:6.1f} TF/s)", flush=True)
+                    except Exception as exc:  # noqa: BLE001
+                        print(f"   forced bn{bn} mh{mh} pair{pair} staged{mode}: {exc}", flush=True)
+            ops.conv_set_tuning()
+            ops.conv_set_epilogue(-1)
     ops.conv_set_epilogue(-1)
 
 
