@@ -77,7 +77,6 @@ struct Conv2Params {
   // round trip of the style gradient through memory.
   int x_row0;                  // input row that lines up with output row 0 (1 when the input buffer
                                // carries a halo row above the band: row-band sharding)
-  int stage_last;              // the last tile of every CTA stages its stores in the (idle) operand ring
   int staged;                  // plain / un-pooling epilogue stores go through the shared-memory
                                // transpose (coalesced 128-byte lines); needs the staging tiles
   int style_kc;                // N / 32 slabs of the 1x1 contraction (0 = off)
@@ -492,15 +491,13 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
           // lanes per pixel) instead of 32 different lines with 16 bytes each.  The scattered form
           // costs ~4 LSU cycles per 16 bytes: with it a dual-output forward layer took 2.5x and an
           // un-pooling dgrad 4x the time of the same MMAs (profiles/r2_epilogue_ab_v1.log).
-          // The epilogue of a CTA's LAST tile is never hidden behind MMAs (on the small feature
-          // maps of a 512x512 image every CTA has exactly one tile), and by then the operand ring
-          // is idle -- the producer has issued its last load and acc_full says every MMA that read
-          // the ring has retired -- so that epilogue borrows ring memory as its staging tiles and
-          // stores coalesced even where the tile has no dedicated staging space (256-wide tiles).
-          const bool last_tile = t + workers >= p.tiles_total;
-          const bool borrow = !p.staged && p.stage_last != 0 && last_tile;
-          const bool staged = p.staged != 0 || borrow;
-          const uint32_t stg = (borrow ? a_base : stage_base) + (warp - kFirstEpiWarp) * 4096;
+          // (Staging the LAST tile of a CTA in the then idle operand ring -- so that the one-tile
+          // CTAs of the small 512x512 feature maps store coalesced too -- was measured and
+          // rejected: those launches are not store-bound, 845 -> 816 steps/s,
+          // profiles/r2_epilogue_ab_512.log.)
+          constexpr bool kCanStage = BLOCK_N <= 128;  // wider tiles: no shared memory to spare
+          const bool staged = kCanStage && p.staged != 0;
+          const uint32_t stg = stage_base + (warp - kFirstEpiWarp) * 4096;
           const int row_m0 = hf * 128 + q * 32;  // first pixel (tile-local) of this warp's 32 rows
           if (p.unpool_code != nullptr) {
             // dgrad whose output pixel is a POOLED pixel: the 2x2 max-pool backward (+ the ReLU gate
@@ -1134,8 +1131,6 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
       p.staged = 1;
     }
   }
-  // last-tile staging in the ring: plain / un-pooling epilogues without dedicated staging tiles
-  p.stage_last = (!staging && !p.staged && N != 16 && g_tuning.staged != 0) ? 1 : 0;
   if (p.uni) {
     // one ring of {A tile, its weight taps}: as deep as shared memory allows, up to 4; 64-wide and
     // 16-wide tiles stay at 2 so that two CTAs share an SM
