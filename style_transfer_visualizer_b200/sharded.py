@@ -132,6 +132,7 @@ class _BandWorkspace:
     gram_ws: list[torch.Tensor] = field(default_factory=list)
     s_mat: list[torch.Tensor] = field(default_factory=list)
     reduce_buf: torch.Tensor | None = None              # [sum C^2 + n_content] one all-reduce
+    raw: list[torch.Tensor] = field(default_factory=list)   # per-layer raw Gram partial / global R
     losses: torch.Tensor | None = None
     scratch: torch.Tensor | None = None
     grad_h: torch.Tensor | None = None                  # [1, 3, band + 2, W]
@@ -171,6 +172,7 @@ class RowBandEngine:
 
         self.halo_mode = "nccl" if os.environ.get("STV_HALO") == "nccl" or self.world == 1 \
             else "nvlink-peer"
+        self._side = torch.cuda.Stream(device=device)   # loss kernels + their all-reduces
         self.bands: list[tuple[int, int]] | None = None   # set per image (plan_bands)
         self.style_targets: list[torch.Tensor] | None = None
         self.content_targets: list[torch.Tensor] | None = None   # own rows, NHWC
@@ -337,6 +339,8 @@ class RowBandEngine:
                 ws.s_mat.append(buf(c, c))
                 total += c * c
             ws.reduce_buf = buf(total + len(self.content_idx))
+            ws.raw = [buf(self.stages[self._stage(idx)].cout, self.stages[self._stage(idx)].cout)
+                      for idx in self.style_idx]
             ws.losses = buf(len(self.style_idx) + len(self.content_idx))
             ws.scratch = buf(2 * nat.reduce_scratch_floats() + 1024)
             ws.img_send = buf(2, 3, width)
@@ -372,7 +376,7 @@ class RowBandEngine:
         return h, w
 
     # ------------------------------------------------------------------ forward
-    def _run_stack(self, x_band: torch.Tensor, ws: _BandWorkspace) -> None:
+    def _run_stack(self, x_band: torch.Tensor, ws: _BandWorkspace, after_stage=None) -> None:  # noqa: ANN001
         """Forward through the band.  Every conv READS the haloed buffer of its input (x_row0 = 1: the
         halo rows supply the neighbours' pixels, zeros at the image edge) and WRITES own rows only,
         with the same fused epilogues as the single-GPU engine: ReLU sign bits, 2x2 max pool +
@@ -404,6 +408,8 @@ class RowBandEngine:
                                  out_post=post, round_flags=2 | int(rp), out_bits=ws.bits[s])
             cur = ws.pool[s] if st.pool_idx is not None else \
                 (ws.post[s] if ws.post[s] is not None else ws.pre[s])
+            if after_stage is not None:
+                after_stage(s, st)
             if s + 1 < n:
                 self._xchg(ws, cur, slot=1 + s)  # halos for the next 3x3 conv
 
@@ -446,31 +452,48 @@ class RowBandEngine:
                                 for idx in self.content_idx]
 
     def forward_losses(self, x_band: torch.Tensor) -> torch.Tensor:
-        """Global losses (identical on every rank): style ascending, then content."""
+        """Global losses (identical on every rank): style ascending, then content.
+
+        The loss work of a tapped layer -- this band's raw Gram partial, its all-reduce over the
+        ranks, clamp / 1/N / MSE / backward seed on the global matrix; the content partial sum and
+        its all-reduce -- is issued on a side stream right after the layer, so all of it except
+        the last layer's overlaps the rest of the forward pass (the communicator is used from the
+        side stream only, in the same order on every rank)."""
         if self.style_targets is None or self.content_targets is None:
             msg = "targets must be set before computing losses."
             raise RuntimeError(msg)
         ws = self._workspace(int(x_band.shape[2]), int(x_band.shape[3]), with_grad=False)
-        self._run_stack(x_band.detach(), ws)
         ns = len(self.style_idx)
-        sums = []
-        for k, idx in enumerate(self.content_idx):
-            f = self._own(ws.pre[self._stage(idx)])
-            ops.content_loss_fwd(f, self.content_targets[k], ws.scratch, ws.losses[ns + k:ns + k + 1])
-            sums.append(ws.losses[ns + k:ns + k + 1] * float(f.numel()))  # mean -> partial sum
-        raws = self._reduce_grams(ws, sums)
-        off = sum(r.numel() for r in raws)
-        for k, idx in enumerate(self.style_idx):
-            s = self._stage(idx)
-            c = self.stages[s].cout
+        main = torch.cuda.current_stream(self.device)
+        side = self._side
+
+        def after_stage(s: int, st) -> None:  # noqa: ANN001
+            style_k = self.style_idx.index(st.conv_idx) if st.conv_idx in self.style_idx else None
+            content_k = self.content_idx.index(st.conv_idx) if st.conv_idx in self.content_idx \
+                else None
+            if style_k is None and content_k is None:
+                return
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
             fh, fw = self._full_rows_at(s)
-            ops.gram_from_r(raws[k], float(c) * fh * fw, ws.scratch, target=self.style_targets[k],
-                            s_out=ws.s_mat[k], loss_out=ws.losses[k:k + 1])
-        for k, idx in enumerate(self.content_idx):
-            s = self._stage(idx)
-            fh, fw = self._full_rows_at(s)
-            total = float(self.stages[s].cout) * fh * fw
-            ws.losses[ns + k:ns + k + 1].copy_(ws.reduce_buf[off + k:off + k + 1] / total)
+            total = float(st.cout) * fh * fw
+            with torch.cuda.stream(side):
+                feats = self._own(ws.pre[s])
+                if style_k is not None:
+                    r = ws.raw[style_k]
+                    ops.gram_partial_r(feats, ws.gram_ws[style_k], r)
+                    dist.all_reduce(r, op=dist.ReduceOp.SUM, group=self.group)
+                    ops.gram_from_r(r, total, ws.scratch, target=self.style_targets[style_k],
+                                    s_out=ws.s_mat[style_k], loss_out=ws.losses[style_k:style_k + 1])
+                if content_k is not None:
+                    slot = ws.losses[ns + content_k:ns + content_k + 1]
+                    ops.content_loss_fwd(feats, self.content_targets[content_k], ws.scratch, slot)
+                    slot.mul_(float(feats.numel()) / total)   # local mean -> share of the global mean
+                    dist.all_reduce(slot, op=dist.ReduceOp.SUM, group=self.group)
+
+        self._run_stack(x_band.detach(), ws, after_stage)
+        main.wait_stream(side)
         return ws.losses
 
     # ------------------------------------------------------------------ backward
@@ -648,11 +671,8 @@ class ShardedFusedStep:
         eng = self.engine
         band, width = int(self.x.shape[2]), int(self.x.shape[3])
         losses = eng.forward_losses(self.x.detach())
-        torch.sum(losses[:self.ns], dim=0, out=self.scores[0])
-        torch.sum(losses[self.ns:], dim=0, out=self.scores[1])
-        torch.mul(self.scores[0], self.style_w, out=self._tmp[0])
-        torch.mul(self.scores[1], self.content_w, out=self._tmp[1])
-        torch.add(self._tmp[0], self._tmp[1], out=self.scores[2])
+        ops.step_scores(losses, self.ns, int(losses.numel()) - self.ns, self.style_w,
+                        self.content_w, self.scores)
         self.grad.copy_(eng.backward_losses(band, width, self.grad_w))
         ops.adam_step_dev(self.x.detach(), self.grad, self.m, self.v, self.adam_state, lr=self.lr,
                           beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
