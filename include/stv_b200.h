@@ -53,6 +53,13 @@ int stv_conv3x3_first_fwd(const float* img_nchw, const float* w /*[64][3][3][3]*
 int stv_conv3x3_first_fwd_bits(const float* img_nchw, const float* w, const float* bias, int H,
                                int W, int Cout, float* out_pre, float* out_post,
                                unsigned* out_bits, int round_pre, void* stream);
+/* conv1_1 forward on the tensor cores: the K = 27 contraction as four tcgen05.mma (TF32 multiply, FP32
+ * accumulate -- what cuDNN does for this layer in the reference's CUDA path), im2col rows built in
+ * shared memory straight from the NCHW image.  Same outputs as stv_conv3x3_first_fwd_bits; in_rows /
+ * in_row0 as in stv_conv3x3_first_fwd_band (0, 0 = plain image).  w: torch layout [64][3][3][3]. */
+int stv_conv3x3_first_fwd_tc(const float* img_nchw, const float* w, const float* bias, int H, int W,
+                             int Cout, int in_rows, int in_row0, float* out_pre, float* out_post,
+                             unsigned* out_bits, int round_pre, void* stream);
 /* 3x3 pad-1 conv on the tensor cores (tcgen05, TF32 multiply, FP32 accumulate).
  * x: NHWC [H][W][Cin], w_fwd from stv_pack_conv_weights, Cin % 32 == 0, Cout % 64 == 0.
  * out_post is always stored rounded to TF32 (it is the next conv's MMA operand); round_pre != 0

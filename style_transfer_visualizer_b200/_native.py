@@ -43,6 +43,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_pack_conv_weights": [_vp, _vp, _vp, _i, _i, _vp],
     "stv_conv3x3_first_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "stv_conv3x3_first_fwd_bits": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "stv_conv3x3_first_fwd_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "stv_conv3x3_fwd_bits": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "stv_conv3x3_fwd_pool_code": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],

@@ -369,6 +369,13 @@ int stv_conv3x3_first_fwd_band(const float* img_nchw, const float* w, const floa
                                round_pre, S(stream), in_rows, in_row0);
 }
 
+int stv_conv3x3_first_fwd_tc(const float* img_nchw, const float* w, const float* bias, int H, int W,
+                             int Cout, int in_rows, int in_row0, float* out_pre, float* out_post,
+                             unsigned* out_bits, int round_pre, void* stream) {
+  return conv_first_fwd_tc_launch(img_nchw, w, bias, H, W, Cout, in_rows, in_row0, out_pre,
+                                  out_post, out_bits, round_pre, S(stream));
+}
+
 int stv_halo_exchange(float* mine, float* up, float* down, int rows, int rows_up, int rows_down,
                       long row_floats, int planes, unsigned* flags_mine, unsigned* flags_up,
                       unsigned* flags_down, unsigned* epoch, unsigned* done, int slot, int wait_ready,

@@ -378,6 +378,39 @@ __device__ __forceinline__ float relu_nan(float x) {
   return r;
 }
 
+// One warp stores its 32 pixels x 32 channels (lane = pixel, v[32] = that pixel's values as raw
+// bits) through a 4 KB shared-memory tile: 16-byte chunks are written swizzled by (row & 7), read
+// back with 8 lanes per pixel, and every st.global.v4 instruction then covers 4 complete 128-byte
+// lines.  xform(bits, k) maps value k before it is staged; row_ptr(rr) is the global address of
+// pixel rr's 32-channel chunk, or nullptr when the pixel lies outside the image.
+template <class Xform, class RowPtr>
+__device__ __forceinline__ void staged_store_32x32(uint32_t stg, int lane, const uint32_t (&v)[32],
+                                                   Xform&& xform, RowPtr&& row_ptr) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(xform(v[4 * j], 4 * j)),
+                 "r"(xform(v[4 * j + 1], 4 * j + 1)), "r"(xform(v[4 * j + 2], 4 * j + 2)),
+                 "r"(xform(v[4 * j + 3], 4 * j + 3))
+                 : "memory");
+  }
+  __syncwarp();
+  const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + sub;
+    float* dst = row_ptr(rr);
+    const uint32_t a = stg + rr * 128 + ((chunk ^ (rr & 7)) << 4);
+    uint4 q4;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w)
+                 : "r"(a)
+                 : "memory");
+    if (dst != nullptr) *reinterpret_cast<uint4*>(dst + 4 * chunk) = q4;
+  }
+  __syncwarp();  // the staging tile is rewritten by the next call
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -63,6 +63,10 @@ int gram_from_r_launch(const float* r, int C, double n_total, const float* targe
 int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
                           int Cout, float* out_pre, float* out_post, unsigned* out_bits,
                           int round_pre, cudaStream_t stream, int in_rows = 0, int in_row0 = 0);
+// conv_first_tc.cu: conv1_1 forward on the tensor cores (TF32, K = 27 padded to 32)
+int conv_first_fwd_tc_launch(const float* img_nchw, const float* w, const float* bias, int H, int W,
+                             int Cout, int in_rows, int in_row0, float* out_pre, float* out_post,
+                             unsigned* out_bits, int round_pre, cudaStream_t stream);
 int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
                             float* dimg_nchw, cudaStream_t stream);
 int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,

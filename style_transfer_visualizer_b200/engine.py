@@ -25,6 +25,9 @@ from . import ops
 # before building a model).
 DEFAULT_COMPACT_BACKWARD = True
 DEFAULT_FUSE_STYLE_BWD = True
+# conv1_1 forward on the tensor cores (TF32 like every other conv, and like cuDNN in the reference's
+# CUDA path) instead of exact-fp32 CUDA cores
+DEFAULT_FIRST_LAYER_TC = True
 
 
 def _on_own_device(method):  # noqa: ANN001, ANN202
@@ -106,6 +109,7 @@ class VggLossEngine:
         # for A/B measurements; stages whose ReLU / pool output is tapped by a loss always use those.
         self.compact_backward = DEFAULT_COMPACT_BACKWARD
         self.fuse_style_bwd = DEFAULT_FUSE_STYLE_BWD
+        self.first_layer_tc = DEFAULT_FIRST_LAYER_TC
 
     # ------------------------------------------------------------------ program construction
     def _build_stages(self, layers: list[nn.Module]) -> list[_Stage]:
@@ -295,7 +299,10 @@ class VggLossEngine:
     def _run_stack(self, x: torch.Tensor, ws: _Workspace, after_stage=None) -> None:  # noqa: ANN001
         cur: torch.Tensor | None = None
         for s, st in enumerate(self.stages):
-            if s == 0:
+            if s == 0 and self.first_layer_tc:
+                ops.conv3x3_first_fwd_tc(x, st.weight, st.bias, ws.pre[0], ws.post[0],
+                                         round_pre=self._round_pre(st), out_bits=ws.bits[0])
+            elif s == 0:
                 ops.conv3x3_first_fwd(x, st.weight, st.bias, ws.pre[0], ws.post[0],
                                       round_pre=self._round_pre(st), out_bits=ws.bits[0])
             elif ws.code[s] is not None:

@@ -58,6 +58,20 @@ def conv3x3_first_fwd(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | N
              nat.ptr(out_pre), nat.ptr(out_post), int(round_pre), _s(img))
 
 
+def conv3x3_first_fwd_tc(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,  # noqa: PLR0913
+                         out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
+                         rows: int | None = None, in_row0: int = 0, round_pre: bool = False,
+                         out_bits: torch.Tensor | None = None) -> None:
+    """conv1_1 forward on the tensor cores (``stv_conv3x3_first_fwd_tc``); ``img`` may be a haloed
+    band ``[1, 3, in_rows, W]`` with ``rows`` output rows starting at input row ``in_row0``."""
+    _chk(img, "img")
+    in_rows = int(img.shape[-2])
+    nat.call("stv_conv3x3_first_fwd_tc", nat.ptr(img), nat.ptr(w), nat.ptr(bias),
+             in_rows if rows is None else rows, int(img.shape[-1]), int(w.shape[0]), in_rows,
+             in_row0, nat.ptr(out_pre), nat.ptr(out_post), nat.ptr(out_bits), int(round_pre),
+             _s(img))
+
+
 def conv3x3_fwd(x: torch.Tensor, w_fwd: torch.Tensor, bias: torch.Tensor | None,  # noqa: PLR0913
                 out_pre: torch.Tensor | None, out_post: torch.Tensor | None, *,
                 round_pre: bool = False, out_pool: torch.Tensor | None = None,

@@ -393,8 +393,12 @@ class RowBandEngine:
             pre = own(ws.pre[s]) if ws.pre[s] is not None else None
             post = own(ws.post[s]) if ws.post[s] is not None else None
             if s == 0:
-                ops.conv3x3_first_fwd_band(ws.x_h, st.weight, st.bias, pre, post, rows=rows,
-                                           in_row0=1, round_pre=rp, out_bits=ws.bits[0])
+                if self.base.first_layer_tc:
+                    ops.conv3x3_first_fwd_tc(ws.x_h, st.weight, st.bias, pre, post, rows=rows,
+                                             in_row0=1, round_pre=rp, out_bits=ws.bits[0])
+                else:
+                    ops.conv3x3_first_fwd_band(ws.x_h, st.weight, st.bias, pre, post, rows=rows,
+                                               in_row0=1, round_pre=rp, out_bits=ws.bits[0])
             elif st.pool_idx is not None:
                 ops.conv3x3_desc(cur, st.w_fwd, rows=rows, x_row0=1, bias=st.bias, out_pre=pre,
                                  round_flags=2 | int(rp), out_pool=own(ws.pool[s]),

@@ -468,6 +468,23 @@ def case_conv_compact() -> bool:
         same = torch.equal(pre, pre2) and torch.equal(post, post2) and \
             torch.equal(unpack_bits(bits, 64), post > 0)
         ok &= report(f"first fwd + sign bits {hh}x{ww}", 0.0 if same else 1.0, 0.0)
+        # tensor-core variant (TF32 operands): close to the exact-fp32 kernel, self-consistent bits
+        pre3 = torch.full_like(pre, float("nan"))
+        post3 = torch.full_like(post, float("nan"))
+        bits3 = torch.full((hh, ww, 2), -1, device=dev, dtype=torch.int32)
+        ops.conv3x3_first_fwd_tc(img, w1, b1, pre3, post3, out_bits=bits3)
+        ok &= report(f"first fwd tensor-core pre  {hh}x{ww}", rel_l2(pre3, pre), 1.5e-3)
+        ok &= report(f"first fwd tensor-core post {hh}x{ww}", rel_l2(post3, post), 1.5e-3)
+        same = torch.equal(unpack_bits(bits3, 64), post3 > 0) and \
+            torch.equal(post3, torch.relu(post3)) and \
+            int((post3.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        ok &= report(f"first fwd tensor-core bits / rounding {hh}x{ww}", 0.0 if same else 1.0, 0.0)
+        # haloed band: rows 1..hh-2 of the same image as a band with one halo row above and below
+        band = img[:, :, 0:hh, :].contiguous()
+        pre4 = torch.full((hh - 2, ww, 64), float("nan"), device=dev)
+        ops.conv3x3_first_fwd_tc(band, w1, b1, pre4, None, rows=hh - 2, in_row0=1)
+        ok &= report(f"first fwd tensor-core band rows {hh}x{ww}",
+                     0.0 if torch.equal(pre4, pre3[1:hh - 1]) else 1.0, 0.0)
 
     for (hh, ww, ci, co) in [(40, 56, 64, 64), (37, 53, 64, 128), (70, 94, 128, 128), (33, 47, 128, 256),
                              (24, 40, 256, 256), (19, 8, 256, 512), (16, 16, 512, 512), (9, 11, 64, 64),
