@@ -298,6 +298,15 @@ int stv_conv_set_tuning(int pair_mode, int a_stages, int b_stages, int taps_per_
  * measured rule (coalesced shared-memory-transposed stores where a value is stored more than once or
  * the epilogue is the bottleneck), 0 = always direct, 1 = coalesced wherever the tile allows. */
 int stv_conv_set_epilogue(int staged_mode);
+/* Split-K second MMA issuer of one-half tiles (calling host thread): -1 = the built-in rule (128-wide
+ * one-half tiles, and 64-wide ones that have their SM to themselves), 0 = never, 1 = wherever the
+ * tile family has the variant.  Results with and without differ in fp32 summation order only. */
+int stv_conv_set_split(int mode);
+/* Replace the rule table's tile plan for ONE layer shape (calling host thread only; sweeps): output
+ * H x W, C -> N channels, backward = 1 for input-gradient launches.  block_n / m_halves / depth /
+ * taps_per_stage: 0 = keep the rule's value; pair: -1 = keep.  H <= 0 clears the table. */
+int stv_conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int m_halves,
+                           int pair, int depth, int taps_per_stage);
 /* Naive CUDA-core NHWC conv, same packed weights; on-device cross-check only. */
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream);

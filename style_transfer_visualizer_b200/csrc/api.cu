@@ -410,6 +410,25 @@ int stv_conv_set_epilogue(int staged_mode) {
   conv_set_epilogue(staged_mode);
   return 0;
 }
+int stv_conv_set_split(int mode) {
+  STV_REQUIRE(mode >= -1 && mode <= 1, "stv_conv_set_split: mode must be -1, 0 or 1");
+  conv_set_split(mode);
+  return 0;
+}
+int stv_conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int m_halves,
+                           int pair, int depth, int taps_per_stage) {
+  if (H > 0) {
+    STV_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256,
+                "stv_conv_plan_override: block_n must be 0, 64, 128 or 256");
+    STV_REQUIRE(m_halves >= 0 && m_halves <= 2 && pair >= -1 && pair <= 1 && depth >= 0 &&
+                    depth <= 8 && (taps_per_stage == 0 || taps_per_stage == 1 || taps_per_stage == 3),
+                "stv_conv_plan_override: parameter out of range");
+  }
+  STV_REQUIRE(conv_plan_override(H, W, C, N, backward, block_n, m_halves, pair, depth,
+                                 taps_per_stage) == 0,
+              "stv_conv_plan_override: table full");
+  return 0;
+}
 int stv_conv_ref(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                  int N, int taps, int relu, float* out, void* stream) {
   return conv_ref_launch(x, w_packed, bias, H, W, C, N, taps, relu, out, S(stream));

@@ -111,14 +111,24 @@ __host__ __device__ constexpr int conv2_epi_warps(int block_n, int mh = 2) {
 // them): tcgen05.commit stalls its thread for ~500 cycles, which starves the tensor pipe when a
 // stage is only 12-24 short (N <= 128) MMAs; the other issuer's MMAs fill that hole
 // (profiles/r1_umma_peak.log: N=64 72 -> 53 cycles per MMA, N=128 87 -> 66).
-__host__ __device__ constexpr int conv2_issuers(int mh) { return mh == 2 ? 2 : 1; }
-__host__ __device__ constexpr int conv2_threads(int block_n, int mh) {
-  return 32 * (1 + conv2_issuers(mh) + conv2_epi_warps(block_n, mh));
+//
+// SPLIT gives ONE-half tiles the same second issuer: the two threads take alternate ring stages
+// (split-K) into two accumulators of the tile, which the epilogue adds.  It is used where a CTA has
+// its SM to itself -- 128-wide one-half tiles (shared memory allows one CTA per SM) and the lone
+// 64-wide CTAs of small feature maps; 64-wide tiles with two co-resident CTAs already have two
+// issuing threads per SM.
+__host__ __device__ constexpr int conv2_issuers(int mh, bool split = false) {
+  return (mh == 2 || split) ? 2 : 1;
+}
+__host__ __device__ constexpr int conv2_threads(int block_n, int mh, bool split = false) {
+  return 32 * (1 + conv2_issuers(mh, split) + conv2_epi_warps(block_n, mh));
 }
 
-template <int BLOCK_N, int MH, bool PAIR, bool STYLE = false>
+template <int BLOCK_N, int MH, bool PAIR, bool STYLE = false, bool SPLIT = false>
 struct Conv2Cfg {
-  static constexpr int kAccW = STYLE ? 2 : 1;  // accumulators per 128-pixel half (conv, style)
+  static_assert(!SPLIT || (MH == 1 && !PAIR && !STYLE && BLOCK_N >= 64), "split-K: one-half tiles");
+  // accumulators per 128-pixel half: (conv, style) or the two split-K partial sums
+  static constexpr int kAccW = (STYLE || SPLIT) ? 2 : 1;
   static constexpr int kTileCols = MH * BLOCK_N * kAccW;
   static constexpr int kAcc = (2 * kTileCols <= 512) ? 2 : 1;
   static constexpr int kTmemColsRaw = kAcc * kTileCols;
@@ -128,17 +138,19 @@ struct Conv2Cfg {
 };
 
 // 64- and 16-wide one-half tiles run as two co-resident CTAs per SM: cap their registers accordingly
-template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false>
-__global__ void __launch_bounds__(conv2_threads(BLOCK_N, MH), (BLOCK_N <= 64 && MH == 1) ? 2 : 1)
+template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false, bool SPLIT = false>
+__global__ void __launch_bounds__(conv2_threads(BLOCK_N, MH, SPLIT),
+                                  (BLOCK_N <= 64 && MH == 1 && !SPLIT) ? 2 : 1)
 conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                         const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_f,
                         const __grid_constant__ CUtensorMap tmap_s, const Conv2Params p) {
-  using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR, STYLE>;
+  using Cfg = Conv2Cfg<BLOCK_N, MH, PAIR, STYLE, SPLIT>;
   constexpr int kTileCols = Cfg::kTileCols;
   constexpr int EW = conv2_epi_warps(BLOCK_N, MH);
-  constexpr int NI = conv2_issuers(MH);
-  constexpr int kThreads2 = conv2_threads(BLOCK_N, MH);
+  constexpr int NI = conv2_issuers(MH, SPLIT);
+  constexpr int kStageUsers = SPLIT ? 1 : NI;  // issuers that consume (and commit) one ring stage
+  constexpr int kThreads2 = conv2_threads(BLOCK_N, MH, SPLIT);
   constexpr int kFirstEpiWarp = 1 + NI;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // tile schedule: a "worker" is a CTA, or a CTA pair
@@ -182,8 +194,14 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // its "accumulator drained" barriers one arrival from each epilogue warp of both CTAs
     const uint32_t np = PAIR ? 2u : 1u;
     // every issuer commits each stage / accumulator it has used
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + 8 * s, np); mbar_init(a_empty + 8 * s, NI); }
-    for (int s = 0; s < BS; ++s) { mbar_init(b_full + 8 * s, np); mbar_init(b_empty + 8 * s, NI); }
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(a_full + 8 * s, np);
+      mbar_init(a_empty + 8 * s, kStageUsers);
+    }
+    for (int s = 0; s < BS; ++s) {
+      mbar_init(b_full + 8 * s, np);
+      mbar_init(b_empty + 8 * s, kStageUsers);
+    }
     for (int s = 0; s < kAcc; ++s) {
       mbar_init(acc_full + 8 * s, NI);
       mbar_init(acc_empty + 8 * s, EW * np);
@@ -314,7 +332,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     // ------------------------------ MMA issuer(s) --------------------------------------------
     // issuer `me` owns the 128-pixel halves hf0 .. hf1-1 of every tile (all of them when NI == 1)
     const int me = warp - 1;
-    const int hf0 = NI == 2 ? me : 0, hf1 = NI == 2 ? me + 1 : MH;
+    const int hf0 = (NI == 2 && !SPLIT) ? me : 0, hf1 = (NI == 2 && !SPLIT) ? me + 1 : MH;
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(PAIR ? 256 : 128, BLOCK_N, 0, 0);
       // Descriptors: the upper word (SBO = 1024, version, SWIZZLE_128B) is constant; the lower word
@@ -324,6 +342,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t lbo_lo = 1u << 16;
       int as = 0, bs = 0, acc = 0;
+      int gs = 0;  // ring stages walked so far (SPLIT: stage gs belongs to issuer gs & 1)
       uint32_t aph = 0, bph = 0, accph = 0;
       const uint32_t row16 = static_cast<uint32_t>(row_bytes) >> 4;
       const uint32_t half16 = (128u >> p.tw_shift) * row16;  // rows per 128-pixel half
@@ -332,10 +351,23 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         if constexpr (PAIR) mbar_wait_cluster(acc_empty + 8 * acc, accph ^ 1);
         else mbar_wait(acc_empty + 8 * acc, accph ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * kTileCols;
+        // SPLIT: this issuer's own partial-sum accumulator (columns me * BLOCK_N ..)
+        const uint32_t d0 = tmem_base + acc * kTileCols + (SPLIT ? me * BLOCK_N : 0);
         uint32_t accum = 0;
         for (int c = 0; c < kc; ++c) {
-          for (int dxi = 0; dxi < ndx; ++dxi) {
+          for (int dxi = 0; dxi < ndx; ++dxi, ++gs) {
+            // SPLIT: alternate ring stages, counted over the whole tile sequence; the ring depth is
+            // even (host), so a ring slot -- and its pair of barriers -- always belongs to the same
+            // issuer and no waiter can fall a barrier phase behind the other issuer's progress
+            if (SPLIT && (gs & 1) != me) {
+              // the other issuer's stage: step over it (and over its weight stages)
+              if (++as == AS) { as = 0; aph ^= 1; }
+              if (!p.uni) {
+                for (int dyi = 0; dyi < ndy; dyi += TPS)
+                  if (++bs == BS) { bs = 0; bph ^= 1; }
+              }
+              continue;
+            }
             mbar_wait(a_full + 8 * as, aph);
             const uint32_t a_lo =
                 (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
@@ -419,6 +451,30 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
     uint32_t accph = 0;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const uint32_t acc_empty_c = PAIR ? mapa_u32(acc_empty, 0) : acc_empty;
+    // SPLIT: a tile with a single ring stage (C = 32, one tap) has only one partial sum, and which
+    // issuer produced it alternates from tile to tile
+    const int tile_stages = kc * ndx;
+    int gs_epi = 0;  // ring stages before the current tile
+    // one 32-column chunk of the tile's accumulator (the sum of the two split-K partials)
+    auto ld_acc = [&](uint32_t taddr, uint32_t (&r)[32]) {
+      if constexpr (SPLIT) {
+        if (tile_stages < 2) {
+          tmem_ld_32x32(taddr + (gs_epi & 1) * BLOCK_N, r);
+        } else {
+          tmem_ld_32x32(taddr, r);
+          uint32_t s2[32];
+          tmem_ld_32x32(taddr + BLOCK_N, s2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(s2[k]));
+          return;
+        }
+      } else {
+        tmem_ld_32x32(taddr, r);
+      }
+      tmem_ld_wait();
+    };
     for (int t = worker; t < p.tiles_total; t += workers) {
       const int nt = t / p.tiles_m;
       const int mt = PAIR ? 2 * (t - nt * p.tiles_m) + static_cast<int>(rank) : t - nt * p.tiles_m;
@@ -477,8 +533,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll 1
             for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
               uint32_t r[32];
-              tmem_ld_32x32(trow + cb, r);
-              tmem_ld_wait();
+              ld_acc(trow + cb, r);
               uint32_t rw[4] = {0u, 0u, 0u, 0u};  // route bits of the four window pixels
               if (valid) {
                 const size_t wq = (static_cast<size_t>(2 * py) * p.W2 + 2 * px) * (p.N >> 5) +
@@ -559,8 +614,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll 1
             for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
               uint32_t r[32];
-              tmem_ld_32x32(trow + cb, r);
-              tmem_ld_wait();
+              ld_acc(trow + cb, r);
               uint32_t gate = 0xFFFFFFFFu;  // dgrad: ReLU gate of this pixel's 32 channels
               if (p.mask_bits != nullptr && valid)
                 gate = __ldg(p.mask_bits + pix * (p.N >> 5) + ((n0 + cb) >> 5));
@@ -680,8 +734,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll 1
           for (int cb = cb0; cb < cb0 + kCols; cb += 32) {
             uint32_t r[32];
-            tmem_ld_32x32(trow + cb, r);
-            tmem_ld_wait();
+            ld_acc(trow + cb, r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t a = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
@@ -780,6 +833,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         else mbar_arrive(acc_empty + 8 * acc);
       }
       if (++acc == kAcc) { acc = 0; accph ^= 1; }
+      gs_epi += tile_stages;
     }
   }
 
@@ -802,9 +856,43 @@ struct ConvTuning {
   int pair_mode = -1;                      // -1: rule table, 0: never, 1: whenever the shape allows
   int a_stages = 0, b_stages = 0, tps = 0;  // ring depth / taps-per-stage overrides (0 = defaults)
   int staged = -1;                          // epilogue stores: -1 rule, 0 direct, 1 coalesced
+  int split = -1;                           // split-K second issuer: -1 rule, 0 never, 1 where legal
 };
 static thread_local ConvTuning g_tuning;
+
+// Per-shape plan overrides (stv_conv_plan_override): the sweep tool replaces the rule table's
+// choice for ONE layer of a running step and times the whole step.  Thread-local like g_tuning.
+struct ConvPlan { int H, W, C, N, backward, block_n, mh, pair, depth, tps; };
+constexpr int kMaxPlans = 64;
+static thread_local ConvPlan g_plans[kMaxPlans];
+static thread_local int g_num_plans = 0;
+int conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int mh, int pair,
+                       int depth, int tps) {
+  if (H <= 0) { g_num_plans = 0; return 0; }
+  for (int i = 0; i < g_num_plans; ++i) {
+    ConvPlan& q = g_plans[i];
+    if (q.H == H && q.W == W && q.C == C && q.N == N && q.backward == backward) {
+      q = ConvPlan{H, W, C, N, backward, block_n, mh, pair, depth, tps};
+      return 0;
+    }
+  }
+  if (g_num_plans == kMaxPlans) return 1;
+  g_plans[g_num_plans++] = ConvPlan{H, W, C, N, backward, block_n, mh, pair, depth, tps};
+  return 0;
+}
+static bool is_backward(const ConvArgs& a) {
+  return a.mask_bits || a.mask_src || a.unpool_code || a.style_x || a.out_nchw3;
+}
+static const ConvPlan* find_plan(const ConvArgs& a) {
+  const int bwd = is_backward(a) ? 1 : 0;
+  for (int i = 0; i < g_num_plans; ++i) {
+    const ConvPlan& q = g_plans[i];
+    if (q.H == a.H && q.W == a.W && q.C == a.C && q.N == a.N && q.backward == bwd) return &q;
+  }
+  return nullptr;
+}
 void conv_set_epilogue(int staged_mode) { g_tuning.staged = staged_mode; }
+void conv_set_split(int mode) { g_tuning.split = mode; }
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
   g_tuning.pair_mode = pair_mode;
   g_tuning.a_stages = a_stages;
@@ -826,11 +914,11 @@ static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int b_ro
          n_total * 4 + 128 + (staging ? conv2_epi_warps(block_n, mh) * 4096 : 0);
 }
 
-template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false>
+template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false, bool SPLIT = false>
 static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Params& p, int grid,
                    cudaStream_t stream, const CUtensorMap* tf = nullptr,
                    const CUtensorMap* ts = nullptr) {
-  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR, STYLE>;
+  auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR, STYLE, SPLIT>;
   const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
                                     Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N, MH,
                                     p.staged || p.mask_src != nullptr || p.add_src != nullptr);
@@ -845,7 +933,7 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(conv2_threads(BLOCK_N, MH));
+  cfg.blockDim = dim3(conv2_threads(BLOCK_N, MH, SPLIT));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -938,6 +1026,9 @@ static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want
       mh = order[i][1];
     }
   }
+  const ConvPlan* plan = find_plan(a);
+  if (plan && plan->block_n > 0 && N % plan->block_n == 0) bn = plan->block_n;
+  if (plan && plan->mh > 0) mh = plan->mh;
   if (a.force_n > 0) bn = a.force_n;
   if (a.force_mh > 0) mh = a.force_mh;
   // CTA pairs (profiles/r1_pair_sweep.log, r1_ring_sweep.log): with half-size weight stages a
@@ -949,7 +1040,8 @@ static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want
   if (N != 16) {
     if (g_tuning.pair_mode >= 0) pair = g_tuning.pair_mode;
     else pair = (a.taps == 9 && (bn == 256 || (bn == 128 && mh == 2))) ? 1 : 0;
-    if (pair && bn == 256 && a.force_mh <= 0) mh = 1;
+    if (plan && plan->pair >= 0) pair = plan->pair;
+    if (pair && bn == 256 && a.force_mh <= 0 && !(plan && plan->mh > 0)) mh = 1;
   }
   const int tw2 = a.force_tw > 0 ? a.force_tw : pick_tw(H, W, mh, want_pool);
   return TileChoice{mh, tw2, 128 * mh / tw2, bn, pair};
@@ -1021,7 +1113,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   p.style_alpha = a.style_alpha;
   // the second accumulator exists for the two tile families the tapped 64- and 128-wide layers
   // use; any other choice (small feature maps narrow the tile) reports "not fusable" to the caller
-  if (style && !((tc.block_n == 64 && tc.mh == 1 && !tc.pair) ||
+  if (style && !((tc.block_n == 64 && (tc.mh == 2 || !tc.pair)) ||
                  (tc.block_n == 128 && tc.mh == 2 && tc.pair)))
     return kConvStyleNotFusable;
   STV_REQUIRE(a.out_code == nullptr || p.out_code != nullptr,
@@ -1062,7 +1154,10 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   const int sms = device_sm_count();
   // ring depths: defaults keep >= ~2000 MMA cycles of weight stages in flight (TMA latency under
   // load) within the shared-memory budget; stv_conv_set_tuning overrides them for sweeps
-  const int env_as = g_tuning.a_stages, env_bs = g_tuning.b_stages, env_tps = g_tuning.tps;
+  const ConvPlan* plan = find_plan(a);
+  const int env_as = (plan && plan->depth > 0) ? plan->depth : g_tuning.a_stages;
+  const int env_bs = (plan && plan->depth > 0) ? plan->depth : g_tuning.b_stages;
+  const int env_tps = (plan && plan->tps > 0) ? plan->tps : g_tuning.tps;
   p.tps = (taps == 9 && (tc.block_n <= 128 || tc.pair)) ? 3 : 1;
   if (env_tps > 0 && taps == 9 && (tc.block_n <= 128 || tc.pair)) p.tps = env_tps;
   const int b_rows = tc.pair ? tc.block_n / 2 : tc.block_n;
@@ -1073,6 +1168,10 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   // their shared memory is full: they keep the direct stores).
   bool staging = staging_needed;
   p.staged = 0;
+  // 64-wide one-half tiles run two CTAs per SM on a 2-deep ring each -- unless there are not even
+  // enough tiles for one CTA per SM (small feature maps): then a lone CTA needs the deep ring to
+  // cover the ~1.7 us re-arm chain (32x32x512 layer at depth 2: 0.9 us per 12-MMA stage).
+  const bool two_per_sm = tc.block_n == 64 && tc.mh == 1 && p.tiles_total > sms;
   // Measured per launch type (profiles/r2_epilogue_ab_v2.log): the transpose pays where a value is
   // stored more than once or the epilogue is the bottleneck -- un-pooling dgrads (4 stores per value:
   // 2.1-3.3x faster), dual-output forward layers (1.4-1.6x), single-output dgrads (+3-8 %) -- and
@@ -1082,7 +1181,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   const bool want_staged = g_tuning.staged < 0 ? staged_pays : g_tuning.staged == 1;
   if (!staging_needed && want_staged && N != 16 && tc.block_n <= 128) {
     auto depth_for = [&](bool stg) {
-      int depth = p.uni ? ((tc.block_n == 64 && tc.mh == 1) ? 2 : 4) : 4;
+      int depth = p.uni ? (two_per_sm ? 2 : 4) : 4;
       if (p.uni && env_as > 0) depth = env_as;
       const int a_st = p.uni ? 0 : (tc.block_n >= 256 ? 2 : 3);
       while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, p.uni ? depth : a_st, depth, p.tps,
@@ -1101,7 +1200,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   if (p.uni) {
     // one ring of {A tile, its weight taps}: as deep as shared memory allows, up to 4; 64-wide and
     // 16-wide tiles stay at 2 so that two CTAs share an SM
-    int depth = (tc.block_n == 64 && tc.mh == 1) ? 2 : 4;
+    int depth = two_per_sm ? 2 : 4;
     if (env_as > 0) depth = env_as;
     while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, depth, depth, p.tps, b_rows, N,
                                          tc.block_n, tc.mh, staging) > 227 * 1024)
@@ -1118,21 +1217,41 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
                             tc.block_n, tc.mh, staging) > 227 * 1024 && p.b_stages > 2)
       --p.b_stages;
   }
+  // Second issuer by split-K (see conv2_issuers) for one-half tiles that have their SM to themselves
+  const bool split_legal = !tc.pair && tc.mh == 1 && !style && p.uni &&
+                           (tc.block_n == 128 || tc.block_n == 64);
+  // rule: wherever the ring is even-deep anyway (the 128-wide 3-tap ring holds three stages: a
+  // two-deep ring costs it more than the second issuer brings)
+  const bool split = split_legal && (g_tuning.split < 0 ? (p.a_stages % 2 == 0 && !two_per_sm)
+                                                        : g_tuning.split == 1);
+  if (split && p.a_stages % 2 != 0) p.a_stages = p.b_stages = p.a_stages - 1;
   const int smem_est =
       conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N, tc.block_n,
                        tc.mh, staging);
-  const int tile_cols = tc.mh * tc.block_n * (style ? 2 : 1);
+  const int tile_cols = tc.mh * tc.block_n * ((style || split) ? 2 : 1);
   const int tmem_cols = (2 * tile_cols <= 512 ? 2 : 1) * tile_cols;
   if (style && !(p.uni && p.tps == 3)) return kConvStyleNotFusable;  // tuning overrides
-  const int ctas_per_sm = (smem_est <= 113 * 1024 && tmem_cols <= 256) ? 2 : 1;
+  const int ctas_per_sm = (!split && smem_est <= 113 * 1024 && tmem_cols <= 256) ? 2 : 1;
   const int work_ctas = tc.pair ? 2 * p.tiles_total : p.tiles_total;
   int grid = work_ctas < sms * ctas_per_sm ? work_ctas : sms * ctas_per_sm;
   if (tc.pair) grid &= ~1;
 
   auto dispatch = [&]() -> int {
   if (style) {
-    if (tc.block_n == 64) return launch2<64, 1, 3, false, true>(tx, twm, p, grid, stream, &tf, &ts);
+    if (tc.block_n == 64 && tc.mh == 1)
+      return launch2<64, 1, 3, false, true>(tx, twm, p, grid, stream, &tf, &ts);
+    if (tc.block_n == 64 && !tc.pair)
+      return launch2<64, 2, 3, false, true>(tx, twm, p, grid, stream, &tf, &ts);
+    if (tc.block_n == 64) return launch2<64, 2, 3, true, true>(tx, twm, p, grid, stream, &tf, &ts);
     return launch2<128, 2, 3, true, true>(tx, twm, p, grid, stream, &tf, &ts);
+  }
+  if (split) {
+    if (tc.block_n == 128) {
+      if (p.tps == 3) return launch2<128, 1, 3, false, false, true>(tx, twm, p, grid, stream);
+      return launch2<128, 1, 1, false, false, true>(tx, twm, p, grid, stream);
+    }
+    if (p.tps == 3) return launch2<64, 1, 3, false, false, true>(tx, twm, p, grid, stream);
+    return launch2<64, 1, 1, false, false, true>(tx, twm, p, grid, stream);
   }
 #define STV_L2(BN, MHV)                                                          \
   if (tc.block_n == BN && tc.mh == MHV && !tc.pair) {                            \

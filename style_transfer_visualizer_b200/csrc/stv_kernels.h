@@ -49,6 +49,9 @@ int conv_igemm2_launch(const ConvArgs& args, cudaStream_t stream);
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps);
 // epilogue store policy of the calling thread: -1 measured rule, 0 direct, 1 coalesced where possible
 void conv_set_epilogue(int staged_mode);
+void conv_set_split(int mode);
+int conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int mh, int pair,
+                       int depth, int tps);
 
 // gram.cu ---------------------------------------------------------------------------------
 size_t gram_workspace_bytes(long hw, int C);

@@ -429,6 +429,18 @@ def conv_set_epilogue(staged_mode: int = -1) -> None:
     nat.call("stv_conv_set_epilogue", int(staged_mode))
 
 
+def conv_set_split(mode: int = -1) -> None:
+    """-1: built-in rule, 0: single issuer for one-half tiles, 1: split-K second issuer wherever legal."""
+    nat.call("stv_conv_set_split", int(mode))
+
+
+def conv_plan_override(h: int = 0, w: int = 0, c: int = 0, n: int = 0, *, backward: bool = False,  # noqa: PLR0913
+                       block_n: int = 0, m_halves: int = 0, pair: int = -1, depth: int = 0,
+                       tps: int = 0) -> None:
+    """Sweep hook: force the tile plan of one layer shape (``h <= 0`` clears all overrides)."""
+    nat.call("stv_conv_plan_override", h, w, c, n, int(backward), block_n, m_halves, pair, depth, tps)
+
+
 def conv_set_pair_mode(mode: int) -> None:
     """-1: built-in rule table, 0: single-CTA conv tiles only, 1: CTA pairs wherever legal."""
     conv_set_tuning(mode)

@@ -36,6 +36,7 @@ def test_conv_cta_pair_matches_single_cta_bit_for_bit(cuda_device) -> None:  # n
     from style_transfer_visualizer_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(11)
+    ops.conv_set_split(0)  # the split-K second issuer sums in a different order (tested below)
     try:
         for h, w, c, n in [(33, 47, 128, 256), (24, 40, 256, 128), (19, 21, 64, 64), (16, 16, 512, 512)]:
             x = torch.randn(h, w, c, device=cuda_device, generator=g)
@@ -67,3 +68,56 @@ def test_conv_cta_pair_matches_single_cta_bit_for_bit(cuda_device) -> None:  # n
                     assert torch.equal(outs[0][1], torch.relu(outs[0][0]))
     finally:
         ops.conv_set_tuning()
+        ops.conv_set_split()
+
+
+@pytest.mark.gpu
+def test_conv_split_k_second_issuer_matches_single_issuer(cuda_device) -> None:  # noqa: ANN001
+    """One-half tiles with the split-K second issuer (two partial accumulators added in the
+    epilogue) against the single-issuer kernel: same products, fp32 summation order differs ->
+    agreement to fp32 round-off of a K = 9 * C term sum (2e-5 of the largest output); every epilogue (plain, gate bits,
+    accumulate, 1x1) and ring depth, an odd number of ring stages per tile included."""
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(12)
+    try:
+        for h, w, c, n, taps in [(24, 40, 256, 128, 9), (19, 21, 64, 64, 9), (16, 16, 512, 512, 9),
+                                 (33, 47, 96, 128, 9), (20, 20, 64, 64, 1), (17, 31, 32, 64, 1),
+                                 (64, 64, 512, 512, 9),
+                                 # more tiles than CTAs: several tiles per CTA, even and odd stage counts
+                                 (128, 160, 64, 128, 9), (128, 160, 96, 64, 9), (128, 320, 96, 128, 9)]:
+            x = torch.randn(h, w, c, device=cuda_device, generator=g)
+            if taps == 9:
+                wt = torch.randn(n, c, 3, 3, device=cuda_device, generator=g) * 0.05
+                wf, _ = ops.pack_conv_weights(wt)
+            else:
+                wf = (torch.randn(1, n, c, device=cuda_device, generator=g) * 0.05).contiguous()
+            bias = torch.randn(n, device=cuda_device, generator=g)
+            mask = torch.randn(h, w, n, device=cuda_device, generator=g)
+            add = torch.randn(h, w, n, device=cuda_device, generator=g)
+            for bn in (128, 64):
+                if n % bn:
+                    continue
+                for depth in (0, 2, 3):
+                    outs = []
+                    for split in (0, 1):
+                        ops.conv_set_split(split)
+                        ops.conv_set_tuning(0, depth, depth, 0)
+                        pre = torch.full((h, w, n), float("nan"), device=cuda_device)
+                        post = torch.full((h, w, n), float("nan"), device=cuda_device)
+                        ops.conv_igemm2_ex(x, wf, taps=taps, bias=bias, out_pre=pre, out_post=post,
+                                           block_n=bn, m_halves=1)
+                        heavy = torch.full((h, w, n), float("nan"), device=cuda_device)
+                        ops.conv_igemm2_ex(x, wf, taps=taps, mask_src=mask, add_src=add,
+                                           out_pre=heavy, block_n=bn, m_halves=1)
+                        outs.append((pre, post, heavy))
+                    scale = float(outs[0][0].abs().max())
+                    for a, b in zip(outs[0], outs[1]):
+                        assert torch.isfinite(b).all()
+                        assert float((a - b).abs().max()) <= 2e-5 * scale + 1e-6, (h, w, c, n, taps, bn, depth)
+                    assert torch.equal(outs[1][1], torch.relu(outs[1][0]))
+    finally:
+        ops.conv_set_tuning()
+        ops.conv_set_split()
