@@ -15,13 +15,28 @@ namespace stv {
 
 constexpr int kFirstCout = 64;
 
-// One thread = kFirstPx consecutive pixels of a row x 16 output channels (quads cq, cq+4, cq+8,
-// cq+12 with cq = lane % 4).  Each weight quad read from shared memory (one LDS.128) feeds
-// 4 * kFirstPx FMAs -- with 8 pixels the kernel is FMA- rather than LDS-bound (with 4 pixels the two
-// pipes were balanced at ~50 % each and the layer ran at 3.0 TB/s of stores) -- and the four cq
-// lanes of a pixel write 64 contiguous bytes (full 32-byte sectors) per store instruction.
-constexpr int kFirstPx = 8;
-__global__ void __launch_bounds__(128)
+// One thread = kFirstPx consecutive pixels of a row x 16 output channels (the four channel quads
+// q = 4 j + cq, cq = lane % 4, so that the four cq lanes of a pixel write 64 contiguous bytes per
+// store instruction), all 16 channels in ONE pass over the 27 taps:
+//   * packed fp32 FMAs (fma.rn.f32x2, two channels per instruction): each half is an ordinary
+//     fma.rn, so the result is bit-identical to a scalar FMA chain in the same tap order;
+//   * the image values of one (channel, row) are loaded, broadcast into (v, v) pairs once and used
+//     by 3 taps x 4 pixels x 8 channel pairs;
+//   * persistent CTAs: the weights are staged in shared memory once per CTA, not once per 32 pixel
+//     groups.
+// Measured at 1080p (profiles/r2_ncu_conv_first.txt):
+//   8 pixels x 4 channels per pass, scalar FMAs, one CTA per 256 pixels: 219 M warp instructions
+//     (51 % FFMA), 59 % issue utilisation, 337 us (3.06 TB/s of stores);
+//   this version with the image loads in front of their FMAs: 144 M instructions, 301 us; the
+//     schedulers waited for the loads (4.7 warps per issue in long-scoreboard stalls) -> all 54
+//     values are loaded first: 272 us (4.06 TB/s).  What is left is the LSU data pipe (64 % busy: a
+//     128-bit shared load costs four wavefronts however many lanes share an address);
+//   16 pixels x one channel quad per thread (a quarter of the weight LDS, full-line stores, sign
+//     bits by redux.sync): 455 us -- rejected.
+constexpr int kFirstPx = 4;
+constexpr int kFirstThreads = 128;
+constexpr int kFirstGroupsPerCta = kFirstThreads / 4;
+__global__ void __launch_bounds__(kFirstThreads, 3)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                       const float* __restrict__ bias, int H, int W, int groups_per_row,
                       int round_pre, float* __restrict__ out_pre, float* __restrict__ out_post,
@@ -31,7 +46,7 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float4 ws[27][kFirstCout / 4];  // ws[k][c/4] = w[c..c+3][k], k = ci*9 + ky*3 + kx
   __shared__ float4 bs[kFirstCout / 4];
-  for (int i = threadIdx.x; i < 27 * kFirstCout; i += 128) {
+  for (int i = threadIdx.x; i < 27 * kFirstCout; i += kFirstThreads) {
     const int c = i / 27, k = i % 27;  // torch layout [Cout][3][3][3]
     reinterpret_cast<float*>(&ws[k][c >> 2])[c & 3] = w[i];
   }
@@ -42,92 +57,106 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
   // the image may be a haloed band: in_rows rows per plane, row in_row0 = output row 0
   const long hw = static_cast<long>(in_rows) * W;
   const int cq = threadIdx.x & 3;
-  const long grp_raw = static_cast<long>(blockIdx.x) * 32 + (threadIdx.x >> 2);
-  // groups past the end stay alive (the sign-bit shuffles below are warp-wide) but store nothing
-  const bool active = grp_raw < static_cast<long>(groups_per_row) * H;
-  const long grp = active ? grp_raw : 0;
-  const int y = static_cast<int>(grp / groups_per_row);
-  const int x0 = static_cast<int>(grp % groups_per_row) * kFirstPx;
+  const long total_groups = static_cast<long>(groups_per_row) * H;
+  // whole warps stay in the loop together (the sign-bit shuffles are warp-wide)
+  for (long base = static_cast<long>(blockIdx.x) * kFirstGroupsPerCta; base < total_groups;
+       base += static_cast<long>(gridDim.x) * kFirstGroupsPerCta) {
+    const long grp_raw = base + (threadIdx.x >> 2);
+    const bool active = grp_raw < total_groups;  // groups past the end compute but store nothing
+    const long grp = active ? grp_raw : 0;
+    const int y = static_cast<int>(grp / groups_per_row);
+    const int x0 = static_cast<int>(grp % groups_per_row) * kFirstPx;
 
-  float in[3][3][kFirstPx + 2];  // [channel][row][x0-1 .. x0+kFirstPx]
+    float2 acc[kFirstPx][8];  // [pixel][channel pair]: pairs 2 j, 2 j + 1 = quad 4 j + cq
 #pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = bs[4 * j + cq];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+      for (int px = 0; px < kFirstPx; ++px) {
+        acc[px][2 * j] = make_float2(b.x, b.y);
+        acc[px][2 * j + 1] = make_float2(b.z, b.w);
+      }
+    }
+    const bool interior = x0 >= 1 && x0 + kFirstPx < W;
+    // all 54 image values of the 3 x 3 x (kFirstPx + 2) neighbourhood first: the loads are in
+    // flight together instead of one (channel, row) at a time in front of its FMAs
+    float raw[9][kFirstPx + 2];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int ci = r / 3, ky = r - 3 * ci;
       const int yy = y + ky - 1 + in_row0;
       const bool rok = (yy >= 0) && (yy < in_rows);
-      const float* row = img + ci * hw + static_cast<long>(yy) * W;
+      const float* row = img + ci * hw + static_cast<long>(rok ? yy : 0) * W;
+      if (interior) {
 #pragma unroll
-      for (int j = 0; j < kFirstPx + 2; ++j) {
-        const int xx = x0 + j - 1;
-        in[ci][ky][j] = (rok && xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
+        for (int j = 0; j < kFirstPx + 2; ++j) raw[r][j] = rok ? __ldg(row + x0 + j - 1) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kFirstPx + 2; ++j) {
+          const int xx = x0 + j - 1;
+          raw[r][j] = (rok && xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      float2 vv[kFirstPx + 2];  // (v, v) of x0-1 .. x0+kFirstPx
+#pragma unroll
+      for (int j = 0; j < kFirstPx + 2; ++j) vv[j] = make_float2(raw[r][j], raw[r][j]);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int k = r * 3 + kx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 wk = ws[k][4 * j + cq];
+          const float2 w01 = make_float2(wk.x, wk.y), w23 = make_float2(wk.z, wk.w);
+#pragma unroll
+          for (int px = 0; px < kFirstPx; ++px) {
+            acc[px][2 * j] = __ffma2_rn(vv[px + kx], w01, acc[px][2 * j]);
+            acc[px][2 * j + 1] = __ffma2_rn(vv[px + kx], w23, acc[px][2 * j + 1]);
+          }
+        }
       }
     }
 
-  const long pix0 = static_cast<long>(y) * W + x0;
-  // sign bits of the post-ReLU values (the ReLU gate of conv1_2's dgrad): word 0 = channels 0..31,
-  // word 1 = channels 32..63 of each of this thread's pixels
-  uint32_t sb0[kFirstPx], sb1[kFirstPx];
-#pragma unroll
-  for (int px = 0; px < kFirstPx; ++px) { sb0[px] = 0u; sb1[px] = 0u; }
-#pragma unroll 1
-  for (int i = 0; i < kFirstCout / 16; ++i) {
-    const int c4 = i * 4 + cq;
-    float4 acc[kFirstPx];
-#pragma unroll
-    for (int px = 0; px < kFirstPx; ++px) acc[px] = bs[c4];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float4 wk = ws[ci * 9 + ky * 3 + kx][c4];
-#pragma unroll
-          for (int px = 0; px < kFirstPx; ++px) {
-            const float v = in[ci][ky][px + kx];
-            acc[px].x = fmaf(v, wk.x, acc[px].x);
-            acc[px].y = fmaf(v, wk.y, acc[px].y);
-            acc[px].z = fmaf(v, wk.z, acc[px].z);
-            acc[px].w = fmaf(v, wk.w, acc[px].w);
-          }
-        }
+    const long pix0 = static_cast<long>(y) * W + x0;
+    // sign bits of the post-ReLU values (the ReLU gate of conv1_2's dgrad): word 0 = channels
+    // 0..31, word 1 = channels 32..63 of each of this thread's pixels
 #pragma unroll
     for (int px = 0; px < kFirstPx; ++px) {
-      if (active && x0 + px < W) {
-        const long o = (pix0 + px) * (kFirstCout / 4) + c4;
-        if (out_pre) {
-          float4 r = acc[px];
+      const bool st = active && x0 + px < W;
+      uint32_t sb0 = 0u, sb1 = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = make_float4(acc[px][2 * j].x, acc[px][2 * j].y, acc[px][2 * j + 1].x,
+                                     acc[px][2 * j + 1].y);
+        const long o = (pix0 + px) * (kFirstCout / 4) + 4 * j + cq;
+        if (out_pre && st) {
+          float4 r = a;
           if (round_pre) {  // pre only feeds the Gram MMA: store it tf32-rounded
             r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
           }
           reinterpret_cast<float4*>(out_pre)[o] = r;
         }
-        if (out_post || out_bits) {
-          float4 r;
-          // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
-          r.x = round_tf32(relu_nan(acc[px].x)); r.y = round_tf32(relu_nan(acc[px].y));
-          r.z = round_tf32(relu_nan(acc[px].z)); r.w = round_tf32(relu_nan(acc[px].w));
-          if (out_post) reinterpret_cast<float4*>(out_post)[o] = r;
-          const uint32_t nib = (r.x > 0.f ? 1u : 0u) | (r.y > 0.f ? 2u : 0u) |
-                               (r.z > 0.f ? 4u : 0u) | (r.w > 0.f ? 8u : 0u);
-          const uint32_t sh = nib << (16 * (i & 1) + 4 * cq);  // channels 16 i + 4 cq .. + 3
-          if (i < 2) sb0[px] |= sh;
-          else sb1[px] |= sh;
-        }
+        // post feeds conv1_2's MMA: store it tf32-rounded (see round_tf32)
+        float4 r;
+        r.x = round_tf32(relu_nan(a.x)); r.y = round_tf32(relu_nan(a.y));
+        r.z = round_tf32(relu_nan(a.z)); r.w = round_tf32(relu_nan(a.w));
+        if (out_post && st) reinterpret_cast<float4*>(out_post)[o] = r;
+        const uint32_t nib = (r.x > 0.f ? 1u : 0u) | (r.y > 0.f ? 2u : 0u) |
+                             (r.z > 0.f ? 4u : 0u) | (r.w > 0.f ? 8u : 0u);
+        // channels 16 j + 4 cq .. + 3
+        if (j < 2) sb0 |= nib << (16 * j + 4 * cq);
+        else sb1 |= nib << (16 * (j - 2) + 4 * cq);
       }
-    }
-  }
-  if (out_bits) {  // warp-uniform
-#pragma unroll
-    for (int px = 0; px < kFirstPx; ++px) {
-      // OR over the four channel-quad lanes of the pixel group (adjacent lanes: cq = lane % 4)
-      sb0[px] |= __shfl_xor_sync(0xffffffffu, sb0[px], 1);
-      sb0[px] |= __shfl_xor_sync(0xffffffffu, sb0[px], 2);
-      sb1[px] |= __shfl_xor_sync(0xffffffffu, sb1[px], 1);
-      sb1[px] |= __shfl_xor_sync(0xffffffffu, sb1[px], 2);
-      if ((px & 3) == cq && active && x0 + px < W)
-        out_bits[pix0 + px] = make_uint2(sb0[px], sb1[px]);
+      if (out_bits) {  // warp-uniform
+        // OR over the four channel-quad lanes of the pixel group (adjacent lanes: cq = lane % 4)
+        sb0 |= __shfl_xor_sync(0xffffffffu, sb0, 1);
+        sb0 |= __shfl_xor_sync(0xffffffffu, sb0, 2);
+        sb1 |= __shfl_xor_sync(0xffffffffu, sb1, 1);
+        sb1 |= __shfl_xor_sync(0xffffffffu, sb1, 2);
+        if (px == cq && st) out_bits[pix0 + px] = make_uint2(sb0, sb1);
+      }
     }
   }
 }
@@ -213,8 +242,10 @@ int conv_first_fwd_launch(const float* img_nchw, const float* w, const float* bi
   STV_REQUIRE((reinterpret_cast<uintptr_t>(out_bits) & 7) == 0, "conv_first_fwd: out_bits alignment");
   const int groups_per_row = (W + kFirstPx - 1) / kFirstPx;
   const long groups = static_cast<long>(groups_per_row) * H;
-  const unsigned blocks = static_cast<unsigned>((groups + 31) / 32);
-  conv_first_fwd_kernel<<<blocks, 128, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
+  const long want = (groups + kFirstGroupsPerCta - 1) / kFirstGroupsPerCta;
+  const long resident = 3L * device_sm_count();  // persistent CTAs: weights staged once each
+  const unsigned blocks = static_cast<unsigned>(want < 2 * resident ? want : 2 * resident);
+  conv_first_fwd_kernel<<<blocks, kFirstThreads, 0, stream>>>(img_nchw, w, bias, H, W, groups_per_row,
                                                     round_pre, out_pre, out_post,
                                                     reinterpret_cast<uint2*>(out_bits),
                                                     in_rows > 0 ? in_rows : H, in_row0);
