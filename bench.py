@@ -265,7 +265,7 @@ def conv_flops(name: str, a: tuple) -> float | None:
         return 2.0 * 9 * a[2] * a[3] * a[4] * a[5]
     if name == "stv_conv3x3_dgrad_bits_style":      # dgrad + the fused 1x1 Gram backward of the layer
         return 2.0 * 9 * a[2] * a[3] * a[4] * a[5] + 2.0 * a[2] * a[3] * a[5] * a[5]
-    if name == "stv_conv3x3_first_dgrad_tc":        # (dy, w16, H, W, Cout, ...): 3 real channels
+    if name in ("stv_conv3x3_first_dgrad_tc", "stv_conv3x3_first_dgrad_rows"):  # (dy, w, H, W, Cout, ...): 3 real channels
         return 2.0 * 9 * a[2] * a[3] * a[4] * 3
     if name == "stv_style_bwd":                     # (x, s, hw, C, ...)
         return 2.0 * a[2] * a[3] * a[3]
@@ -422,8 +422,8 @@ def hbm_kernel_rooflines(model, x, device, peaks: dict) -> list[dict]:  # noqa: 
     timed("conv_first_fwd_kernel (+sign bits)", 4.0 * n + 2 * 4.0 * 64 * h * w + 8.0 * h * w,
           lambda: ops.conv3x3_first_fwd(x.detach(), st0.weight, st0.bias, ws.pre[0], ws.post[0],
                                         out_bits=ws.bits[0]))
-    timed("conv_igemm2<16> first-layer dgrad", 4.0 * 64 * h * w + 4.0 * n,
-          lambda: ops.conv3x3_first_dgrad_tc(ws.d_y[0], st0.w_dgrad, g))
+    timed("conv_first_dgrad_tc_kernel (first-layer dgrad)", 4.0 * 64 * h * w + 4.0 * n,
+          lambda: ops.conv3x3_first_dgrad_rows(ws.d_y[0], st0.w_dgrad, g))
     k0 = 0
     t0 = eng._tap_tensor(ws, eng.style_idx[k0])  # noqa: SLF001
     timed("gram_partial + finalize (C=64)", 4.0 * t0.numel(),

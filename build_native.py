@@ -8,7 +8,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "style_transfer_visualizer_b200" / "csrc"
 OUT = ROOT / "style_transfer_visualizer_b200" / "lib" / "libstv_b200.so"
-SOURCES = ["api.cu", "conv_igemm2.cu", "gram.cu", "conv_direct.cu", "conv_first_tc.cu", "elementwise.cu",
+SOURCES = ["api.cu", "conv_igemm2.cu", "gram.cu", "conv_direct.cu", "conv_first_tc.cu", "conv_first_dgrad_tc.cu", "elementwise.cu",
            "lbfgs.cu", "halo.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -126,6 +126,13 @@ int stv_conv3x3_first_dgrad(const float* dy, const float* w /*[64][3][3][3]*/, i
 int stv_conv3x3_first_dgrad_tc(const float* dy, const float* w16_dgrad, int H, int W, int Cout,
                                float* dimg_nchw, void* stream);
 
+/* The same gradient with the x taps folded into the GEMM's N (each dy patch is loaded once instead
+ * of once per x shift; the three x-shifted partial results are added in the epilogue):
+ * w_rows = [3 row taps t][16 rows n = kx * 3 + ci (9 real)][64 co] = w[co][ci][2 - t][kx],
+ * tf32-rounded, rows 9..15 zero.  This is the product path. */
+int stv_conv3x3_first_dgrad_rows(const float* dy, const float* w_rows, int H, int W, int Cout,
+                                 float* dimg_nchw, void* stream);
+
 /* ---- pooling / ReLU (torchvision MaxPool2d(2,2), nn.ReLU; core_model.py:134-135) ----------- */
 int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream);
 /* dx = route(dy) to the first max of each 2x2 window; relu_mask != 0 additionally gates by x > 0. */

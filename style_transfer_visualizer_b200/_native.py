@@ -54,6 +54,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_conv3x3_dgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "stv_conv3x3_first_dgrad": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "stv_conv3x3_first_dgrad_tc": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "stv_conv3x3_first_dgrad_rows": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "stv_maxpool2_fwd": [_vp, _i, _i, _i, _vp, _vp],
     "stv_maxpool2_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "stv_relu_fwd": [_vp, _l, _vp, _vp],

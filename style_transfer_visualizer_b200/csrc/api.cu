@@ -225,6 +225,11 @@ int stv_conv3x3_first_dgrad_tc(const float* dy, const float* w16_dgrad, int H, i
   return conv_igemm2_launch(a, S(stream));
 }
 
+int stv_conv3x3_first_dgrad_rows(const float* dy, const float* w_rows, int H, int W, int Cout,
+                                 float* dimg_nchw, void* stream) {
+  return conv_first_dgrad_tc_launch(dy, w_rows, H, W, Cout, dimg_nchw, S(stream));
+}
+
 int stv_maxpool2_fwd(const float* x, int H, int W, int C, float* y, void* stream) {
   return maxpool2_fwd_launch(x, H, W, C, y, S(stream));
 }

@@ -72,6 +72,9 @@ int conv_first_fwd_tc_launch(const float* img_nchw, const float* w, const float*
                              unsigned* out_bits, int round_pre, cudaStream_t stream);
 int conv_first_dgrad_launch(const float* dy, const float* w, int H, int W, int Cout,
                             float* dimg_nchw, cudaStream_t stream);
+// conv_first_dgrad_tc.cu: conv1_1 input gradient, x taps folded into N (dy patch loaded once)
+int conv_first_dgrad_tc_launch(const float* dy, const float* w_rows, int H, int W, int Cout,
+                               float* dimg_nchw, cudaStream_t stream);
 int conv_ref_launch(const float* x, const float* w_packed, const float* bias, int H, int W, int C,
                     int N, int taps, int relu, float* out, cudaStream_t stream);
 

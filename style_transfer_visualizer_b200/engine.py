@@ -156,7 +156,7 @@ class VggLossEngine:
         if first.cin != 3 or first.cout != 64:
             msg = f"first convolution must be 3->64 channels (got {first.cin}->{first.cout})"
             raise ValueError(msg)
-        first.w_dgrad = ops.pack_first_dgrad_weights(first.weight)  # [9, 16, 64] for the N=16 kernel
+        first.w_dgrad = ops.pack_first_dgrad_rows(first.weight)  # [3, 16, 64]: x taps folded into N
         for st in stages[1:]:
             if st.cin % 64 or st.cout % 64:
                 msg = (f"layer {st.conv_idx}: tensor-core conv needs channel counts that are "
@@ -529,7 +529,7 @@ class VggLossEngine:
                 main.wait_event(early[s])
             else:
                 self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
-        ops.conv3x3_first_dgrad_tc(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_img)
+        ops.conv3x3_first_dgrad_rows(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_img)
         return ws.grad_img
 
     # ------------------------------------------------------------------ introspection

@@ -196,6 +196,25 @@ def pack_first_dgrad_weights(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_first_dgrad_rows(w: torch.Tensor) -> torch.Tensor:
+    """conv1_1 weights ``[64, 3, 3, 3]`` -> ``[3, 16, 64]`` for ``conv3x3_first_dgrad_rows``:
+    ``out[t][kx * 3 + ci][co] = w[co][ci][2 - t][kx]`` (tf32-rounded), rows 9..15 zero."""
+    _wf, wd = pack_conv_weights(w)          # wd[ky' * 3 + kx'][ci][co] = w[co][ci][2 - ky'][2 - kx']
+    out = torch.zeros(3, 16, w.shape[0], device=w.device, dtype=torch.float32)
+    for t in range(3):
+        for kx in range(3):
+            out[t, kx * 3:kx * 3 + 3, :] = wd[t * 3 + 2 - kx]
+    return out
+
+
+def conv3x3_first_dgrad_rows(dy: torch.Tensor, w_rows: torch.Tensor, dimg: torch.Tensor) -> None:
+    """conv1_1 input gradient, NHWC ``dy`` -> NCHW ``dimg`` (x taps folded into the GEMM's N)."""
+    _chk(dy, "dy")
+    h, wd, cout = dy.shape
+    nat.call("stv_conv3x3_first_dgrad_rows", nat.ptr(dy), nat.ptr(w_rows), h, wd, cout,
+             nat.ptr(dimg), _s(dy))
+
+
 def conv3x3_first_dgrad_tc(dy: torch.Tensor, w16: torch.Tensor, dimg: torch.Tensor) -> None:
     _chk(dy, "dy")
     h, wd, cout = dy.shape

@@ -555,7 +555,7 @@ class RowBandEngine:
             else:
                 tap_grads(False)
             self._xchg(ws, d_y, slot=s, grads=True)  # halos of the finished gradient feed the next dgrad
-        ops.conv3x3_first_dgrad_tc(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_h)
+        ops.conv3x3_first_dgrad_rows(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_h)
         return ws.grad_h[:, :, 1:-1, :]
 
 

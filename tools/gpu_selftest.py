@@ -321,13 +321,18 @@ def case_conv2() -> bool:
     dx = prev.clone()
     ops.conv3x3_dgrad(nhwc(dy), wd, dx, relu_src=act, accumulate=True)
     ok &= report("igemm2 dgrad + relu gate + accumulate", rel_l2(dx, refd * (act > 0) + prev), 2e-3)
-    for (hh, ww) in [(64, 64), (33, 47), (135, 250)]:
+    for (hh, ww) in [(64, 64), (33, 47), (135, 250), (8, 8), (5, 14), (9, 15), (17, 29), (272, 3840)]:
         w1 = torch.randn(64, 3, 3, 3, device=dev, generator=g) * 0.2
         dy1 = torch.randn(1, 64, hh, ww, device=dev, generator=g)
         ref1 = torch.nn.grad.conv2d_input((1, 3, hh, ww), w1, dy1, padding=1)
         dimg = torch.full((1, 3, hh, ww), float("nan"), device=dev)
         ops.conv3x3_first_dgrad_tc(nhwc(dy1), ops.pack_first_dgrad_weights(w1), dimg)
         ok &= report(f"first dgrad (tensor core, N=16) {hh}x{ww}", rel_l2(dimg, ref1), 2e-3)
+        # x taps folded into N (the product path): same operands, same tolerance; every pixel written
+        dimg2 = torch.full((1, 3, hh, ww), float("nan"), device=dev)
+        ops.conv3x3_first_dgrad_rows(nhwc(dy1), ops.pack_first_dgrad_rows(w1), dimg2)
+        ok &= report(f"first dgrad (x taps in N) {hh}x{ww}", rel_l2(dimg2, ref1), 2e-3)
+        ok &= report(f"first dgrad (x taps in N) vs N=16 kernel {hh}x{ww}", rel_l2(dimg2, dimg), 2e-6)
     for c, hw in ((64, 33 * 47), (128, 64 * 64), (512, 67 * 120), (256, 1024 * 8 + 8)):
         xf = torch.randn(hw, c, device=dev, generator=g)
         sm = torch.randn(c, c, device=dev, generator=g)
@@ -790,6 +795,9 @@ def case_perf() -> bool:
     w16 = ops.pack_first_dgrad_weights(w1)
     ms = _time(lambda: ops.conv3x3_first_dgrad_tc(pre, w16, dimg))
     print(f"PERF conv_first_dgrad_tc 1080p: {ms:.3f} ms {(pre.numel() + img.numel()) * 4 / ms / 1e6:.0f} GB/s")
+    wrows = ops.pack_first_dgrad_rows(w1)
+    ms = _time(lambda: ops.conv3x3_first_dgrad_rows(pre, wrows, dimg))
+    print(f"PERF conv_first_dgrad_rows 1080p: {ms:.3f} ms {(pre.numel() + img.numel()) * 4 / ms / 1e6:.0f} GB/s")
     p = img.flatten().clone()
     gr = torch.randn_like(p)
     m = torch.zeros_like(p)
