@@ -309,6 +309,10 @@ int stv_conv_set_epilogue(int staged_mode);
  * one-half tiles, and 64-wide ones that have their SM to themselves), 0 = never, 1 = wherever the
  * tile family has the variant.  Results with and without differ in fp32 summation order only. */
 int stv_conv_set_split(int mode);
+/* Weight-stationary mode of the 64 -> 64 layers (the CTA pair keeps all 9 x 2 weight blocks in
+ * shared memory, ring stages carry activations only): -1 = built-in rule, 0 = never (A/B runs).
+ * Results are bit-identical either way. */
+int stv_conv_set_resident(int mode);
 /* Replace the rule table's tile plan for ONE layer shape (calling host thread only; sweeps): output
  * H x W, C -> N channels, backward = 1 for input-gradient launches.  block_n / m_halves / depth /
  * taps_per_stage: 0 = keep the rule's value; pair: -1 = keep.  H <= 0 clears the table. */

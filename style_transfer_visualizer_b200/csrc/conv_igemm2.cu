@@ -79,6 +79,12 @@ struct Conv2Params {
                                // carries a halo row above the band: row-band sharding)
   int staged;                  // plain / un-pooling epilogue stores go through the shared-memory
                                // transpose (coalesced 128-byte lines); needs the staging tiles
+  // Weight-stationary mode (64 -> 64 layers): all 9 x C/32 weight blocks of the CTA's N tile (and the
+  // style slabs) are loaded ONCE into shared memory before the first tile, ring stages carry the
+  // activation patch only.  These layers are bound by L2 -> SM traffic (~12 TB/s over all slices),
+  // and more than half of it was the same 147 KB of weights re-read for every 128-pixel tile.
+  int w_resident;
+  int w_res_bytes;             // bytes of the resident region (replaces the weight ring)
   int style_kc;                // N / 32 slabs of the 1x1 contraction (0 = off)
   int style_a_bytes;           // th * tw * 128: an F patch has no halo rows
   const float* style_alpha;    // gl, device scalar
@@ -158,16 +164,19 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   constexpr int kAcc = Cfg::kAcc;
   const int AS = p.a_stages, BS = p.b_stages;
-  const int num_bars = 2 * AS + 2 * BS + 2 * kAcc;
+  // (+2, not +1, for w_full: what follows the barriers is read as float4 and must stay 16-byte aligned)
+  const int num_bars = 2 * AS + 2 * BS + 2 * kAcc + 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + AS * p.a_stage_bytes;
-  const uint32_t bar_base = b_base + BS * TPS * Cfg::kBBytes;
+  const uint32_t bar_base =
+      b_base + (p.w_resident ? static_cast<uint32_t>(p.w_res_bytes) : BS * TPS * Cfg::kBBytes);
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * AS;
   const uint32_t b_full = a_empty + 8 * AS, b_empty = b_full + 8 * BS;
   const uint32_t acc_full = b_empty + 8 * BS, acc_empty = acc_full + 8 * kAcc;
+  const uint32_t w_full = acc_empty + 8 * kAcc;  // resident weights have landed
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
       smem_gen + (bar_base - smem_base) + 8 * num_bars);
   // bias for all N output channels, staged once (epilogue reads it as smem broadcasts)
@@ -206,6 +215,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       mbar_init(acc_full + 8 * s, NI);
       mbar_init(acc_empty + 8 * s, EW * np);
     }
+    mbar_init(w_full, np);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -226,6 +236,31 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.w_resident && warp == 0 && lane == 0) {
+    // weights are never written by a kernel of the step: fetch them under the previous kernel's tail.
+    // Block order = the ring's: ((c * 3 + dx) * TPS + dy) so that the issuer addresses a resident
+    // "slot" c * 3 + dx exactly like a ring stage; style slabs follow.
+    const uint32_t w_full_c = PAIR ? mapa_u32(w_full, 0) : w_full;
+    const int n0 = static_cast<int>(rank) * Cfg::kBRows;
+    const uint32_t bytes = static_cast<uint32_t>((kc * ndx * TPS + p.style_kc) * Cfg::kBBytes);
+    if constexpr (PAIR) mbar_expect_tx_cluster(w_full_c, bytes);
+    else mbar_expect_tx(w_full, bytes);
+    for (int c = 0; c < kc; ++c)
+      for (int dxi = 0; dxi < ndx; ++dxi)
+#pragma unroll
+        for (int u = 0; u < TPS; ++u) {
+          const uint32_t dst = b_base + ((c * ndx + dxi) * TPS + u) * Cfg::kBBytes;
+          if constexpr (PAIR) tma_load_2d_pair(dst, &tmap_w, w_full_c, c << 5, (u * ndx + dxi) * p.N + n0);
+          else tma_load_2d(dst, &tmap_w, w_full, c << 5, (u * ndx + dxi) * p.N + n0);
+        }
+    if constexpr (STYLE) {
+      for (int c = 0; c < p.style_kc; ++c) {
+        const uint32_t dst = b_base + (kc * ndx * TPS + c) * Cfg::kBBytes;
+        if constexpr (PAIR) tma_load_2d_pair(dst, &tmap_s, w_full_c, c << 5, n0);
+        else tma_load_2d(dst, &tmap_s, w_full, c << 5, n0);
+      }
+    }
+  }
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch, bias staging -- none of it touches activations) may overlap the tail of the previous
   // kernel in the stream; from here on we read / write tensors it may still be using.  (Issuing
@@ -254,7 +289,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             mbar_wait(a_empty + 8 * as, aph ^ 1);
             const int cur = as;
             const uint32_t a_bytes = STV_DBG(p, 2) ? 0u : static_cast<uint32_t>(p.a_stage_bytes);
-            const uint32_t b_bytes = STV_DBG(p, 1) ? 0u : static_cast<uint32_t>(TPS * Cfg::kBBytes);
+            const uint32_t b_bytes = (STV_DBG(p, 1) || p.w_resident)
+                                         ? 0u : static_cast<uint32_t>(TPS * Cfg::kBBytes);
             const uint32_t tx_a = a_bytes + (p.uni ? b_bytes : 0u);
             if (tx_a == 0) {
               if constexpr (PAIR) mbar_arrive_cluster(a_full_c + 8 * cur);
@@ -307,7 +343,8 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
         if constexpr (STYLE) {
           // Gram backward of the tapped layer as extra K steps of the same tile: stage =
           // {F patch (no halo), 32-channel slab of S rows n0..}; unified ring only
-          const uint32_t tx_s = static_cast<uint32_t>(p.style_a_bytes + Cfg::kBBytes);
+          const uint32_t tx_s =
+              static_cast<uint32_t>(p.style_a_bytes + (p.w_resident ? 0 : Cfg::kBBytes));
           for (int c = 0; c < p.style_kc; ++c) {
             mbar_wait(a_empty + 8 * as, aph ^ 1);
             const int cur = as;
@@ -315,13 +352,15 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
               mbar_expect_tx_cluster(a_full_c + 8 * cur, tx_s);
               tma_load_3d_pair(a_base + cur * p.a_stage_bytes, &tmap_f, a_full_c + 8 * cur, c << 5,
                                tx0, ty0);
-              tma_load_2d_pair(b_base + cur * TPS * Cfg::kBBytes, &tmap_s, a_full_c + 8 * cur,
-                               c << 5, n0);
+              if (!p.w_resident)
+                tma_load_2d_pair(b_base + cur * TPS * Cfg::kBBytes, &tmap_s, a_full_c + 8 * cur,
+                                 c << 5, n0);
             } else {
               mbar_expect_tx(a_full + 8 * cur, tx_s);
               tma_load_3d(a_base + cur * p.a_stage_bytes, &tmap_f, a_full + 8 * cur, c << 5, tx0,
                           ty0);
-              tma_load_2d(b_base + cur * TPS * Cfg::kBBytes, &tmap_s, a_full + 8 * cur, c << 5, n0);
+              if (!p.w_resident)
+                tma_load_2d(b_base + cur * TPS * Cfg::kBBytes, &tmap_s, a_full + 8 * cur, c << 5, n0);
             }
             if (++as == AS) { as = 0; aph ^= 1; }
           }
@@ -346,6 +385,10 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
       uint32_t aph = 0, bph = 0, accph = 0;
       const uint32_t row16 = static_cast<uint32_t>(row_bytes) >> 4;
       const uint32_t half16 = (128u >> p.tw_shift) * row16;  // rows per 128-pixel half
+      if (p.w_resident) {
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+      }
       for (int t = worker; t < p.tiles_total; t += workers) {
         // epilogue (of both CTAs) has drained this accumulator
         if constexpr (PAIR) mbar_wait_cluster(acc_empty + 8 * acc, accph ^ 1);
@@ -374,7 +417,7 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             for (int dyi = 0; dyi < ndy; dyi += TPS) {
               if (!p.uni) mbar_wait(b_full + 8 * bs, bph);
               tc_fence_after();
-              const uint32_t b_slot = p.uni ? as : bs;
+              const uint32_t b_slot = p.w_resident ? c * ndx + dxi : (p.uni ? as : bs);
               const uint32_t b_lo =
                   (((b_base + b_slot * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
@@ -415,8 +458,9 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             mbar_wait(a_full + 8 * as, aph);
             tc_fence_after();
             const uint32_t a_lo = (((a_base + as * p.a_stage_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
-            const uint32_t b_lo =
-                (((b_base + as * (TPS * Cfg::kBBytes)) & 0x3FFFFu) >> 4) | lbo_lo;
+            const uint32_t s_addr = p.w_resident ? b_base + (kc * ndx * TPS + c) * Cfg::kBBytes
+                                                 : b_base + as * (TPS * Cfg::kBBytes);
+            const uint32_t b_lo = ((s_addr & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
             for (int hf = hf0; hf < hf1; ++hf) {
 #pragma unroll
@@ -857,6 +901,7 @@ struct ConvTuning {
   int a_stages = 0, b_stages = 0, tps = 0;  // ring depth / taps-per-stage overrides (0 = defaults)
   int staged = -1;                          // epilogue stores: -1 rule, 0 direct, 1 coalesced
   int split = -1;                           // split-K second issuer: -1 rule, 0 never, 1 where legal
+  int resident = -1;                        // weight-stationary 64 -> 64 layers: -1 rule, 0 never
 };
 static thread_local ConvTuning g_tuning;
 
@@ -893,6 +938,7 @@ static const ConvPlan* find_plan(const ConvArgs& a) {
 }
 void conv_set_epilogue(int staged_mode) { g_tuning.staged = staged_mode; }
 void conv_set_split(int mode) { g_tuning.split = mode; }
+void conv_set_resident(int mode) { g_tuning.resident = mode; }
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
   g_tuning.pair_mode = pair_mode;
   g_tuning.a_stages = a_stages;
@@ -908,10 +954,12 @@ static int current_device() {
 
 // b_rows: weight rows one CTA stages per tap (the N tile, or half of it for a CTA pair)
 // staging: the transposing epilogue (ReLU gate / accumulate) needs one 4 KB tile per epilogue warp
+// res_bytes > 0: weight-stationary mode, the resident region replaces the weight ring
 static int conv2_smem_bytes(int a_stage_bytes, int as, int bs, int tps, int b_rows,
-                            int n_total, int block_n, int mh, int staging) {
-  return as * a_stage_bytes + bs * tps * b_rows * 128 + 8 * (2 * as + 2 * bs + 4) + 32 + 1024 +
-         n_total * 4 + 128 + (staging ? conv2_epi_warps(block_n, mh) * 4096 : 0);
+                            int n_total, int block_n, int mh, int staging, int res_bytes = 0) {
+  return as * a_stage_bytes + (res_bytes > 0 ? res_bytes : bs * tps * b_rows * 128) +
+         8 * (2 * as + 2 * bs + 6) + 32 + 1024 + n_total * 4 + 128 +
+         (staging ? conv2_epi_warps(block_n, mh) * 4096 : 0);
 }
 
 template <int BLOCK_N, int MH, int TPS, bool PAIR, bool STYLE = false, bool SPLIT = false>
@@ -921,7 +969,8 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR, STYLE, SPLIT>;
   const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
                                     Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N, MH,
-                                    p.staged || p.mask_src != nullptr || p.add_src != nullptr);
+                                    p.staged || p.mask_src != nullptr || p.add_src != nullptr,
+                                    p.w_resident ? p.w_res_bytes : 0);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   const int dev = current_device();
   // per kernel instantiation AND per device: the opt-in is a property of the (function, context)
@@ -1026,6 +1075,12 @@ static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want
       mh = order[i][1];
     }
   }
+  // 64 -> 64 layers with several tiles per CTA run weight-stationary (Conv2Params::w_resident) on
+  // CTA pairs: each CTA keeps its half of the weights (74 KB) next to a 3-4 deep ring of 256-pixel
+  // activation patches
+  const bool stationary = g_tuning.resident != 0 && N == 64 && C == 64 && a.taps == 9 &&
+                          count_tiles(H, W, N, 2, pick_tw(H, W, 2, want_pool), 64) >= 2L * sms;
+  if (stationary) { bn = 64; mh = 2; }
   const ConvPlan* plan = find_plan(a);
   if (plan && plan->block_n > 0 && N % plan->block_n == 0) bn = plan->block_n;
   if (plan && plan->mh > 0) mh = plan->mh;
@@ -1039,7 +1094,7 @@ static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want
   int pair = 0;
   if (N != 16) {
     if (g_tuning.pair_mode >= 0) pair = g_tuning.pair_mode;
-    else pair = (a.taps == 9 && (bn == 256 || (bn == 128 && mh == 2))) ? 1 : 0;
+    else pair = (a.taps == 9 && (bn == 256 || (bn == 128 && mh == 2) || (stationary && bn == 64 && mh == 2))) ? 1 : 0;
     if (plan && plan->pair >= 0) pair = plan->pair;
     if (pair && bn == 256 && a.force_mh <= 0 && !(plan && plan->mh > 0)) mh = 1;
   }
@@ -1166,12 +1221,19 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   // (gate / accumulate) epilogue always has them; the plain and un-pooling epilogues of tiles up to
   // 128 wide take them when that does not cost a ring stage (256-wide tiles are tensor-bound and
   // their shared memory is full: they keep the direct stores).
-  bool staging = staging_needed;
-  p.staged = 0;
+  // weight-stationary mode: the N tile's 9 * C/32 weight blocks (+ style slabs) stay in shared memory
+  int res_bytes = 0;
+  if (g_tuning.resident != 0 && taps == 9 && p.uni && p.tps == 3 && N == tc.block_n && N == 64 &&
+      C == 64 && tc.mh == 2)
+    res_bytes = (9 * (C / 32) + (style ? N / 32 : 0)) * b_rows * 128;
   // 64-wide one-half tiles run two CTAs per SM on a 2-deep ring each -- unless there are not even
   // enough tiles for one CTA per SM (small feature maps): then a lone CTA needs the deep ring to
   // cover the ~1.7 us re-arm chain (32x32x512 layer at depth 2: 0.9 us per 12-MMA stage).
   const bool two_per_sm = tc.block_n == 64 && tc.mh == 1 && p.tiles_total > sms;
+  bool staging = staging_needed;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  staging = staging_needed;
+  p.staged = 0;
   // Measured per launch type (profiles/r2_epilogue_ab_v2.log): the transpose pays where a value is
   // stored more than once or the epilogue is the bottleneck -- un-pooling dgrads (4 stores per value:
   // 2.1-3.3x faster), dual-output forward layers (1.4-1.6x), single-output dgrads (+3-8 %) -- and
@@ -1185,14 +1247,14 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
       if (p.uni && env_as > 0) depth = env_as;
       const int a_st = p.uni ? 0 : (tc.block_n >= 256 ? 2 : 3);
       while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, p.uni ? depth : a_st, depth, p.tps,
-                                           b_rows, N, tc.block_n, tc.mh, stg) > 227 * 1024)
+                                           b_rows, N, tc.block_n, tc.mh, stg, res_bytes) > 227 * 1024)
         --depth;
       return depth;
     };
     // (the explicit policy override may trade a ring stage for the staging tiles: experiments)
     if (p.uni && (depth_for(true) == depth_for(false) || g_tuning.staged == 1) &&
         conv2_smem_bytes(p.a_stage_bytes, depth_for(true), depth_for(true), p.tps, b_rows, N,
-                         tc.block_n, tc.mh, true) <= 227 * 1024) {
+                         tc.block_n, tc.mh, true, res_bytes) <= 227 * 1024) {
       staging = true;
       p.staged = 1;
     }
@@ -1203,7 +1265,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
     int depth = two_per_sm ? 2 : 4;
     if (env_as > 0) depth = env_as;
     while (depth > 2 && conv2_smem_bytes(p.a_stage_bytes, depth, depth, p.tps, b_rows, N,
-                                         tc.block_n, tc.mh, staging) > 227 * 1024)
+                                         tc.block_n, tc.mh, staging, res_bytes) > 227 * 1024)
       --depth;
     p.a_stages = depth;
     p.b_stages = depth;
@@ -1217,6 +1279,18 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
                             tc.block_n, tc.mh, staging) > 227 * 1024 && p.b_stages > 2)
       --p.b_stages;
   }
+  // a resident weight block that leaves fewer than three activation stages (or does not fit at
+  // all) is not worth it: size the rings again for the streaming mode
+  if (res_bytes > 0 && (p.a_stages < 3 ||
+                        conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N,
+                                         tc.block_n, tc.mh, staging, res_bytes) > 227 * 1024)) {
+    res_bytes = 0;
+    continue;
+  }
+  break;
+  }
+  p.w_resident = res_bytes > 0 ? 1 : 0;
+  p.w_res_bytes = res_bytes;
   // Second issuer by split-K (see conv2_issuers) for one-half tiles that have their SM to themselves
   const bool split_legal = !tc.pair && tc.mh == 1 && !style && p.uni &&
                            (tc.block_n == 128 || tc.block_n == 64);
@@ -1227,7 +1301,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   if (split && p.a_stages % 2 != 0) p.a_stages = p.b_stages = p.a_stages - 1;
   const int smem_est =
       conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps, b_rows, N, tc.block_n,
-                       tc.mh, staging);
+                       tc.mh, staging, res_bytes);
   const int tile_cols = tc.mh * tc.block_n * ((style || split) ? 2 : 1);
   const int tmem_cols = (2 * tile_cols <= 512 ? 2 : 1) * tile_cols;
   if (style && !(p.uni && p.tps == 3)) return kConvStyleNotFusable;  // tuning overrides

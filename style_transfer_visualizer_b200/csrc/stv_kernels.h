@@ -50,6 +50,7 @@ void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps);
 // epilogue store policy of the calling thread: -1 measured rule, 0 direct, 1 coalesced where possible
 void conv_set_epilogue(int staged_mode);
 void conv_set_split(int mode);
+void conv_set_resident(int mode);
 int conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int mh, int pair,
                        int depth, int tps);
 

@@ -121,3 +121,54 @@ def test_conv_split_k_second_issuer_matches_single_issuer(cuda_device) -> None: 
     finally:
         ops.conv_set_tuning()
         ops.conv_set_split()
+
+
+@pytest.mark.gpu
+def test_conv_weight_stationary_is_bit_identical(cuda_device) -> None:  # noqa: ANN001
+    """64 -> 64 layers with several tiles per CTA keep their weights resident in shared memory (CTA
+    pairs, ring stages carry activations only).  Same MMAs in the same order as the streaming
+    kernel of the same tile family: every output -- forward with fused pool / route bits / sign
+    bits, bit-gated dgrad, dgrad with the fused style backward -- must match bit for bit; and the
+    forward agrees with the CUDA-core cross-check."""
+    import torch
+
+    from style_transfer_visualizer_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(13)
+    try:
+        for h, w in [(300, 400), (301, 403), (512, 512)]:
+            x = torch.randn(h, w, 64, device=cuda_device, generator=g).relu()
+            wt = torch.randn(64, 64, 3, 3, device=cuda_device, generator=g) * 0.05
+            wf, wd = ops.pack_conv_weights(wt)
+            bias = torch.randn(64, device=cuda_device, generator=g)
+            dy = torch.randn(h, w, 64, device=cuda_device, generator=g)
+            gate = ops.relu_bits_buffer(h, w, 64, cuda_device)
+            gate.random_(-2 ** 31, 2 ** 31 - 1)
+            feat = torch.randn(h, w, 64, device=cuda_device, generator=g)
+            smat = torch.randn(64, 64, device=cuda_device, generator=g)
+            smat = ((smat + smat.t()) * 0.5).contiguous()
+            gl = torch.tensor([0.37], device=cuda_device)
+            outs = []
+            for mode in (0, -1):
+                ops.conv_set_resident(mode)
+                ops.conv_plan_override()
+                if mode == 0:  # same tile family as the stationary rule picks: two halves on a CTA pair
+                    for bwd in (False, True):
+                        ops.conv_plan_override(h, w, 64, 64, backward=bwd, block_n=64, m_halves=2, pair=1)
+                post = torch.full((h, w, 64), float("nan"), device=cuda_device)
+                pool = torch.full((h // 2, w // 2, 64), float("nan"), device=cuda_device)
+                bits = ops.relu_bits_buffer(h, w, 64, cuda_device).fill_(-1)
+                code = ops.pool_code_buffer(h, w, 64, cuda_device).fill_(-1)
+                ops.conv3x3_fwd(x, wf, bias, None, post, out_pool=pool, out_bits=bits, out_code=code)
+                dx = torch.full((h, w, 64), float("nan"), device=cuda_device)
+                ops.conv3x3_dgrad(dy, wd, dx, relu_bits=gate)
+                dxs = torch.full((h, w, 64), float("nan"), device=cuda_device)
+                ops.conv3x3_dgrad_style(dy, wd, dxs, relu_bits=gate, feat=feat, s_mat=smat, grad_w=gl)
+                outs.append((post, pool, bits, code, dx, dxs))
+            for a, b in zip(outs[0], outs[1]):
+                assert torch.equal(a, b)
+            ref = ops.conv_ref(x, wf, bias, taps=9, relu=True)
+            assert torch.allclose(outs[1][0], ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+    finally:
+        ops.conv_set_resident()
+        ops.conv_plan_override()

@@ -66,11 +66,21 @@ def main() -> None:
     ap.add_argument("--layers", default="", help="comma list of layer indices to sweep (default all)")
     ap.add_argument("--ab-split", action="store_true",
                     help="only compare the split-K second issuer: off / rule / everywhere legal")
+    ap.add_argument("--ab-resident", action="store_true",
+                    help="only compare weight-stationary 64->64 layers: off / rule")
     args = ap.parse_args()
     from style_transfer_visualizer_b200 import ops
 
     h, w = (1080, 1920) if args.size == "1080p" else (int(args.size), int(args.size))
     model, x, opt = build(h, w)
+    if args.ab_resident:
+        for rnd in range(2):
+            for mode, name in ((0, "weights streamed"), (-1, "rule (64->64 weight-stationary)")):
+                ops.conv_set_resident(mode)
+                us = time_step(model, x, opt, args.reps)
+                print(f"round {rnd} {name:32s}: {us:8.1f} us/step ({1e6 / us:6.1f} steps/s)", flush=True)
+        ops.conv_set_resident()
+        return
     if args.ab_split:
         for rnd in range(2):
             for mode, name in ((0, "single issuer"), (-1, "rule"), (1, "split wherever legal")):
