@@ -1078,7 +1078,10 @@ static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want
   // 64 -> 64 layers with several tiles per CTA run weight-stationary (Conv2Params::w_resident) on
   // CTA pairs: each CTA keeps its half of the weights (74 KB) next to a 3-4 deep ring of 256-pixel
   // activation patches
+  // (input-gradient launches only: the forward 64 -> 64 layer with its fused-pool epilogue runs
+  // 45 % slower on a CTA pair, 481 vs 331 us at 1080p, profiles/r2_launches_1080p_step_v3.csv)
   const bool stationary = g_tuning.resident != 0 && N == 64 && C == 64 && a.taps == 9 &&
+                          is_backward(a) &&
                           count_tiles(H, W, N, 2, pick_tw(H, W, 2, want_pool), 64) >= 2L * sms;
   if (stationary) { bn = 64; mh = 2; }
   const ConvPlan* plan = find_plan(a);
@@ -1224,7 +1227,7 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   // weight-stationary mode: the N tile's 9 * C/32 weight blocks (+ style slabs) stay in shared memory
   int res_bytes = 0;
   if (g_tuning.resident != 0 && taps == 9 && p.uni && p.tps == 3 && N == tc.block_n && N == 64 &&
-      C == 64 && tc.mh == 2)
+      C == 64 && tc.mh == 2 && tc.pair)
     res_bytes = (9 * (C / 32) + (style ? N / 32 : 0)) * b_rows * 128;
   // 64-wide one-half tiles run two CTAs per SM on a 2-deep ring each -- unless there are not even
   // enough tiles for one CTA per SM (small feature maps): then a lone CTA needs the deep ring to
