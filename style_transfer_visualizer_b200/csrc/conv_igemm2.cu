@@ -1078,8 +1078,9 @@ static TileChoice choose_tiles(const ConvArgs& a, bool heavy_epilogue, bool want
   // 64 -> 64 layers with several tiles per CTA run weight-stationary (Conv2Params::w_resident) on
   // CTA pairs: each CTA keeps its half of the weights (74 KB) next to a 3-4 deep ring of 256-pixel
   // activation patches
-  // (input-gradient launches only: the forward 64 -> 64 layer with its fused-pool epilogue runs
-  // 45 % slower on a CTA pair, 481 vs 331 us at 1080p, profiles/r2_launches_1080p_step_v3.csv)
+  // (input-gradient launches only: the forward 64 -> 64 layer is bound by its fused-pool epilogue,
+  // 481 us on a weight-stationary CTA pair vs 475 us as it was at 1080p,
+  // profiles/r2_l2_traffic_1080p_step_v3.csv vs r2_ncu_conv_gram_metrics_1080p_v3.csv)
   const bool stationary = g_tuning.resident != 0 && N == 64 && C == 64 && a.taps == 9 &&
                           is_backward(a) &&
                           count_tiles(H, W, N, 2, pick_tw(H, W, 2, want_pool), 64) >= 2L * sms;

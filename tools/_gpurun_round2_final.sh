@@ -1,6 +1,5 @@
 # final single-GPU validation + evidence of the round
 mkdir -p gpurun_out
-timeout 600 python tools/epilogue_ab_512.py > gpurun_out/r2_epilogue_ab_512.log 2>&1; cat gpurun_out/r2_epilogue_ab_512.log | tail -60
 timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu_final.log 2>&1; tail -6 gpurun_out/r2_pytest_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
 python bench.py > gpurun_out/r2_bench_default_final.json 2> gpurun_out/r2_bench_default_final.err; echo "bench rc=$?"
@@ -28,6 +27,8 @@ PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches_bench_512.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
 python tools/summarize_launches.py gpurun_out/r2_launches_bench_512.csv | head -24
 for sz in 512 1080p; do
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_launches_${sz}_step_v2.csv python tools/profile_step.py --size $sz --steps 1 > gpurun_out/ncu_${sz}.log 2>&1
-python tools/summarize_launches.py gpurun_out/r2_launches_${sz}_step_v2.csv | head -26
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_launches_${sz}_step_v3.csv python tools/profile_step.py --size $sz --steps 1 > gpurun_out/ncu_${sz}.log 2>&1
+python tools/summarize_launches.py gpurun_out/r2_launches_${sz}_step_v3.csv | head -26
+ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -k regex:"conv_igemm2|gram_partial|conv_first|relu_fwd_bits" --csv --log-file gpurun_out/r2_ncu_conv_gram_metrics_${sz}_v3.csv python tools/profile_step.py --size $sz --steps 1 > gpurun_out/ncu_m${sz}.log 2>&1
+python tools/summarize_metrics.py gpurun_out/r2_ncu_conv_gram_metrics_${sz}_v3.csv
 done
