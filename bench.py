@@ -274,7 +274,7 @@ def conv_flops(name: str, a: tuple) -> float | None:
 
 def profile_dominant_kernel(model, x, steps: int) -> dict:  # noqa: ANN001
     """CUDA-event timing of EVERY tensor-core conv launch of the step (3x3 fwd incl. the pool-fused
-    ones, 3x3 dgrad incl. the un-pooling ones, the N=16 first-layer dgrad, the 1x1 style backward)
+    ones, 3x3 dgrad incl. the un-pooling ones, the first-layer dgrad, the 1x1 style backward)
     over `steps` eager executions.  One event pair brackets every RUN of consecutive conv launches
     on the stream (a run ends at the next non-conv kernel), so launches that follow each other in
     the real step keep their programmatic-dependent-launch overlap, as they do in the graph-replayed
@@ -544,7 +544,7 @@ def measure_single_image(wl_key: str, args, info, device, sampler, *, full: bool
     out["roofline"] = {
         "bound": "tensor",
         "kernel": "conv_igemm2_tf32_kernel (all tcgen05 conv launches of the step: 3x3 fwd incl. "
-                  "pool-fused, 3x3 dgrad incl. un-pooling, N=16 first-layer dgrad, 1x1 style-bwd)",
+                  "pool-fused, 3x3 dgrad incl. un-pooling, first-layer dgrad, 1x1 style-bwd)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
         "frac_vs_sustained": achieved / (peaks["bf16_sustained"] / 2.0),
