@@ -32,7 +32,11 @@ def build(*, force: bool = False, verbose: bool = False, experiments: bool = Fal
     if not force and not experiments and not needs_rebuild():
         return OUT
     OUT.parent.mkdir(parents=True, exist_ok=True)
-    cmd = ["nvcc", *FLAGS, *(["-DSTV_EXPERIMENTS"] if experiments else []),
+    import os
+    import shlex
+
+    extra = shlex.split(os.environ.get("STV_NVCC_EXTRA", ""))  # A/B builds of tools/ scripts only
+    cmd = ["nvcc", *FLAGS, *extra, *(["-DSTV_EXPERIMENTS"] if experiments else []),
            *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT),
            *[str(CSRC / s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True, check=False)

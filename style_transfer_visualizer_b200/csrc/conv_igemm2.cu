@@ -680,11 +680,13 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                   v.y = fmaf(__uint_as_float(r[4 * j + 1]), alpha, b.y);
                   v.z = fmaf(__uint_as_float(r[4 * j + 2]), alpha, b.z);
                   v.w = fmaf(__uint_as_float(r[4 * j + 3]), alpha, b.w);
-                  const uint32_t g4 = gate >> (4 * j);
-                  v.x = (g4 & 1u) ? v.x : 0.f;
-                  v.y = (g4 & 2u) ? v.y : 0.f;
-                  v.z = (g4 & 4u) ? v.z : 0.f;
-                  v.w = (g4 & 8u) ? v.w : 0.f;
+                  if (p.mask_bits != nullptr) {  // (uniform: forward launches skip the selects)
+                    const uint32_t g4 = gate >> (4 * j);
+                    v.x = (g4 & 1u) ? v.x : 0.f;
+                    v.y = (g4 & 2u) ? v.y : 0.f;
+                    v.z = (g4 & 4u) ? v.z : 0.f;
+                    v.w = (g4 & 8u) ? v.w : 0.f;
+                  }
                   if constexpr (STYLE) {  // the loss gradient of the tapped layer is not gated
                     v.x = fmaf(__uint_as_float(r2[4 * j + 0]), gl, v.x);
                     v.y = fmaf(__uint_as_float(r2[4 * j + 1]), gl, v.y);
@@ -726,9 +728,9 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
                       for (int e = 0; e < 4; ++e) {
                         const float nb = __shfl_xor_sync(0xffffffffu, ov[e], 1);
-                        const float m0 = (nb > ov[e] || nb != nb) ? nb : ov[e];  // row maximum
+                        const float m0 = fmax_nan(nb, ov[e]);  // row maximum
                         const float mo = __shfl_xor_sync(0xffffffffu, m0, p.tw);
-                        const float m = (mo > m0 || mo != mo) ? mo : m0;
+                        const float m = fmax_nan(mo, m0);
                         mx[e] = m;
                         const bool first = (ov[e] == m) && (m > 0.f) && !(odd_x && nb == m) &&
                                            !(odd_y && mo == m);

@@ -372,6 +372,12 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 // ReLU with torch's NaN behaviour: relu(NaN) = NaN (fmaxf would return 0 and hide a diverged run
 // from the reference's non-finite checks, optimization.py:375-391).
+// max with torch's NaN behaviour (NaN if either operand is NaN), one instruction
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ float relu_nan(float x) {
   float r;
   asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
