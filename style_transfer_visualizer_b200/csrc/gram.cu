@@ -22,11 +22,16 @@
 namespace stv {
 
 constexpr int kGramThreads = 192;
-constexpr int kGramPix = 32;                       // pixels (K) per pipeline stage
+#ifndef STV_GRAM_PIX
+#define STV_GRAM_PIX 64
+#endif
+// pixels (K) per pipeline stage: 64 = 8 MMAs per tcgen05.commit (with 32 the ~350-cycle commit stall
+// of the issuing thread outweighed the 4 x 66 cycles of MMAs it followed: 4.2 TB/s, 36 % tensor pipe)
+constexpr int kGramPix = STV_GRAM_PIX;
 constexpr int kGramChunkBytes = kGramPix * 128;    // one {32ch x 32pix} box
 constexpr int kGramOperandBytes = 4 * kGramChunkBytes;
 constexpr int kGramStageBytes = 2 * kGramOperandBytes;
-constexpr int kGramStages = 4;
+constexpr int kGramStages = kGramPix >= 64 ? 3 : 4;  // 3 x 64 KB or 4 x 32 KB of operands in flight
 constexpr int kGramBarOffset = kGramStages * kGramStageBytes;
 constexpr int kGramSmemTotal = kGramBarOffset + (2 * kGramStages + 1) * 8 + 16 + 1024;
 
