@@ -503,6 +503,7 @@ def test_bench_accounting_helpers() -> None:
     for name in bench.CONV_DGRAD:
         assert bench.conv_flops(name, (0, 0, h, w, cout, cin)) == fwd
     assert bench.conv_flops("stv_conv3x3_first_dgrad_tc", (0, 0, h, w, 64)) == 2.0 * 9 * h * w * 64 * 3
+    assert bench.conv_flops("stv_conv3x3_first_dgrad_rows", (0, 0, h, w, 64)) == 2.0 * 9 * h * w * 64 * 3
     assert bench.conv_flops("stv_style_bwd", (0, 0, 100, 64)) == 2.0 * 100 * 64 * 64
     assert bench.conv_flops("stv_adam_step", ()) is None
     # every conv entry point the native layer exports is covered by the accounting
@@ -527,3 +528,35 @@ def test_band_rows_and_arena_layout() -> None:
     bands = plan_bands(2160, 8)
     assert [b - a for a, b in bands] == [272] * 7 + [256]
     assert all(a % 16 == 0 for a, _ in bands) and bands[-1][1] == 2160
+
+
+def test_first_layer_dgrad_rows_formulation_matches_autograd() -> None:
+    """The identity behind ``conv_first_dgrad_tc.cu`` (x taps folded into the GEMM's N), in fp64
+    on the CPU: with ``w_rows[t][kx*3+ci][co] = w[co][ci][2-t][kx]`` (include/stv_b200.h),
+    ``U[y][x'][kx][ci] = sum_{t,co} dY[y-1+t][x'][co] * w_rows[t][kx*3+ci][co]`` and
+    ``dimg[y][x][ci] = U[y][x+1][0][ci] + U[y][x][1][ci] + U[y][x-1][2][ci]`` equal the input
+    gradient of the reference's first Conv2d (zero padding at the borders)."""
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(5)
+    h, w_, co = 7, 9, 64
+    wt = rng.standard_normal((co, 3, 3, 3))
+    dy = rng.standard_normal((1, co, h, w_))
+    ref = torch.nn.grad.conv2d_input((1, 3, h, w_), torch.from_numpy(wt), torch.from_numpy(dy),
+                                     padding=1)[0].numpy()                      # [3, H, W]
+    w_rows = np.zeros((3, 16, co))
+    for t in range(3):
+        for kx in range(3):
+            for ci in range(3):
+                w_rows[t, kx * 3 + ci] = wt[:, ci, 2 - t, kx]
+    dyp = np.zeros((h + 2, w_ + 2, co))
+    dyp[1:-1, 1:-1] = dy[0].transpose(1, 2, 0)                                  # NHWC, zero halo
+    u = np.zeros((h, w_ + 2, 16))                                               # x' = -1 .. W
+    for t in range(3):
+        u += np.einsum("yxc,nc->yxn", dyp[t:t + h], w_rows[t])
+    out = np.zeros((3, h, w_))
+    for ci in range(3):
+        out[ci] = u[:, 2:, 0 + ci] + u[:, 1:-1, 3 + ci] + u[:, :-2, 6 + ci]
+    assert np.allclose(out, ref, rtol=1e-10, atol=1e-10)
+    assert not w_rows[:, 9:].any()
