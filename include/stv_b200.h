@@ -313,6 +313,10 @@ int stv_conv_set_split(int mode);
  * shared memory, ring stages carry activations only): -1 = built-in rule, 0 = never (A/B runs).
  * Results are bit-identical either way. */
 int stv_conv_set_resident(int mode);
+/* Fused 2x2 max pool of tiles up to 128 wide through the shared-memory staging tile (one lane holds
+ * a whole window: no shuffles): -1 = built-in rule, 0 = never (the shuffle form; A/B runs).  Results
+ * are bit-identical either way. */
+int stv_conv_set_pool_smem(int mode);
 /* Replace the rule table's tile plan for ONE layer shape (calling host thread only; sweeps): output
  * H x W, C -> N channels, backward = 1 for input-gradient launches.  block_n / m_halves / depth /
  * taps_per_stage: 0 = keep the rule's value; pair: -1 = keep.  H <= 0 clears the table. */

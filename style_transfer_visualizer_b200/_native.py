@@ -93,6 +93,7 @@ _SIGNATURES: dict[str, list] = {
     "stv_conv_plan_override": [_i] * 10,
     "stv_conv_set_split": [_i],
     "stv_conv_set_resident": [_i],
+    "stv_conv_set_pool_smem": [_i],
     "stv_conv_ref": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
 
@@ -146,7 +147,7 @@ def stream_ptr(device: torch.device | None = None) -> int:
 
 # kernels enqueued per entry point (everything else launches exactly one)
 _KERNELS_PER_CALL = {"stv_gram_loss_fwd": 3, "stv_gram_partial_r": 2, "stv_gram_from_r": 2, "stv_content_loss_fwd": 2, "stv_dot": 2,
-                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_halo_exchange": 1, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0, "stv_conv_set_epilogue": 0, "stv_conv_plan_override": 0, "stv_conv_set_split": 0, "stv_conv_set_resident": 0, "stv_conv_set_tuning": 0,
+                     "stv_absmax_sum": 2, "stv_adam_step_dev": 2, "stv_halo_exchange": 1, "stv_lbfgs_step": 5, "stv_lbfgs_workspace_floats": 0, "stv_abi_version": 0, "stv_conv_set_epilogue": 0, "stv_conv_plan_override": 0, "stv_conv_set_split": 0, "stv_conv_set_resident": 0, "stv_conv_set_pool_smem": 0, "stv_conv_set_tuning": 0,
                      "stv_device_check": 0}
 _launches = [0]
 

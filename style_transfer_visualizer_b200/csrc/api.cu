@@ -425,6 +425,11 @@ int stv_conv_set_resident(int mode) {
   conv_set_resident(mode);
   return 0;
 }
+int stv_conv_set_pool_smem(int mode) {
+  STV_REQUIRE(mode >= -1 && mode <= 0, "stv_conv_set_pool_smem: mode must be -1 or 0");
+  conv_set_pool_smem(mode);
+  return 0;
+}
 int stv_conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int m_halves,
                            int pair, int depth, int taps_per_stage) {
   if (H > 0) {

@@ -77,6 +77,8 @@ struct Conv2Params {
   // round trip of the style gradient through memory.
   int x_row0;                  // input row that lines up with output row 0 (1 when the input buffer
                                // carries a halo row above the band: row-band sharding)
+  int pool_smem;               // fused pool through the staging tile: one lane sees a whole 2x2
+                               // window (no shuffles); needs the staging tiles
   int staged;                  // plain / un-pooling epilogue stores go through the shared-memory
                                // transpose (coalesced 128-byte lines); needs the staging tiles
   // Weight-stationary mode (64 -> 64 layers): all 9 x C/32 weight blocks of the CTA's N tile (and the
@@ -649,6 +651,24 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
             const size_t pool_off =
                 (static_cast<size_t>(py >> 1) * Wo + (px >> 1)) * p.N + n0;
             const bool direct = !staged;  // scattered 16-byte stores straight from the registers
+            // Pool through the staging tile (p.pool_smem): the warp's 32 pixels x 32 channels of
+            // post-ReLU values are transposed through shared memory so that ONE lane holds the four
+            // pixels of a 2x2 window for 8 channels: window k = lane % 8 (the warp's 32 pixels are 8
+            // windows), channels 8 * (lane / 8) .. + 7.  Maxima and the first-maximum routing rule
+            // become plain register compares (~3 instructions per value instead of two shuffles and
+            // ~14 compare / select instructions: the shuffle form made conv1_2 forward spend 480 us
+            // on 219 us of MMAs, profiles/r2_ncu_conv1_2_fwd_summary.txt), the pooled pixel is
+            // written as 4 lanes x 32 contiguous bytes, and the routing bits travel back to the
+            // pixel-owning lanes as bytes through the same tile.
+            const bool pool_smem = kCanStage && pool && p.pool_smem != 0;
+            const int wk = lane & 7, wcg = lane >> 3;
+            const int wq = wk >> (p.tw_shift - 1), wr = wk & ((p.tw >> 1) - 1);
+            const int wp00 = ((wq * 2) << p.tw_shift) + wr * 2;  // warp-local pixel of the window's corner
+            const int wm = row_m0 + wp00;
+            const int wyy = ty0 + (wm >> p.tw_shift), wxx = tx0 + (wm & (p.tw - 1));
+            const bool w_ok = (wyy >> 1) < Ho && (wxx >> 1) < Wo && !STV_DBG(p, 4);
+            const size_t w_off =
+                (static_cast<size_t>(wyy >> 1) * Wo + (wxx >> 1)) * p.N + n0 + 8 * wcg;
             auto row_ptr = [&](float* base, int cb, int rr) -> float* {
               const int mm = row_m0 + rr;
               const int yy = ty0 + (mm >> p.tw_shift), xx = tx0 + (mm & (p.tw - 1));
@@ -717,7 +737,12 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                       *reinterpret_cast<float4*>(p.out_post + row_off + col) = o;
                     bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) |
                              (o.w > 0.f ? 8u : 0u)) << (4 * j);
-                    if (pool) {  // warp-uniform branch: every lane takes part in the shuffles
+                    if (pool_smem) {
+                      const uint32_t sa = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+                      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(o.x),
+                                   "f"(o.y), "f"(o.z), "f"(o.w)
+                                   : "memory");
+                    } else if (pool) {  // warp-uniform branch: every lane takes part in the shuffles
                       // 2x2 window = lanes {l, l^1 (x neighbour), l^tw, l^tw^1 (next / previous
                       // row)}: two shuffles per value give every lane the window maximum.  A lane
                       // routes the pooled gradient iff it holds the FIRST maximum in ATen's scan
@@ -743,6 +768,55 @@ conv_igemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                     }
                   }
                 }
+              }
+              if (pool_smem) {
+                __syncwarp();
+                float w4[4][8];  // [window pixel a, b, c, d in ATen's scan order][channel]
+#pragma unroll
+                for (int wp = 0; wp < 4; ++wp) {
+                  const int prow = wp00 + (wp >> 1) * p.tw + (wp & 1);
+#pragma unroll
+                  for (int hc = 0; hc < 2; ++hc) {
+                    const uint32_t sa = stg + prow * 128 + (((2 * wcg + hc) ^ (prow & 7)) << 4);
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(w4[wp][4 * hc]), "=f"(w4[wp][4 * hc + 1]),
+                                   "=f"(w4[wp][4 * hc + 2]), "=f"(w4[wp][4 * hc + 3])
+                                 : "r"(sa)
+                                 : "memory");
+                  }
+                }
+                float mx[8];
+                uint32_t rbyte[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float m = fmax_nan(fmax_nan(w4[0][e], w4[1][e]), fmax_nan(w4[2][e], w4[3][e]));
+                  mx[e] = m;
+                  // the FIRST maximum in scan order routes, and only a positive one (ReLU gate)
+                  const bool pos = m > 0.f;
+                  const bool ea = w4[0][e] == m, eb = w4[1][e] == m, ec = w4[2][e] == m,
+                             ed = w4[3][e] == m;
+                  rbyte[0] |= ((pos && ea) ? 1u : 0u) << e;
+                  rbyte[1] |= ((pos && eb && !ea) ? 1u : 0u) << e;
+                  rbyte[2] |= ((pos && ec && !ea && !eb) ? 1u : 0u) << e;
+                  rbyte[3] |= ((pos && ed && !ea && !eb && !ec) ? 1u : 0u) << e;
+                }
+                if (w_ok) {
+                  float4* dst = reinterpret_cast<float4*>(p.out_pool + w_off + cb);
+                  dst[0] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+                  dst[1] = make_float4(mx[4], mx[5], mx[6], mx[7]);
+                }
+                if (want_code) {
+                  __syncwarp();  // every lane has its window in registers: the tile can be reused
+#pragma unroll
+                  for (int wp = 0; wp < 4; ++wp) {
+                    const int prow = wp00 + (wp >> 1) * p.tw + (wp & 1);
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(stg + prow * 4 + wcg), "r"(rbyte[wp])
+                                 : "memory");
+                  }
+                  __syncwarp();
+                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(route) : "r"(stg + lane * 4) : "memory");
+                }
+                __syncwarp();  // the staged stores below (and the next chunk) rewrite the tile
               }
               if (p.out_bits != nullptr && valid)
                 p.out_bits[pix * (p.N >> 5) + ((n0 + cb) >> 5)] = bits;
@@ -904,6 +978,7 @@ struct ConvTuning {
   int staged = -1;                          // epilogue stores: -1 rule, 0 direct, 1 coalesced
   int split = -1;                           // split-K second issuer: -1 rule, 0 never, 1 where legal
   int resident = -1;                        // weight-stationary 64 -> 64 layers: -1 rule, 0 never
+  int pool_smem = -1;                       // fused pool through the staging tile: -1 rule, 0 never
 };
 static thread_local ConvTuning g_tuning;
 
@@ -941,6 +1016,7 @@ static const ConvPlan* find_plan(const ConvArgs& a) {
 void conv_set_epilogue(int staged_mode) { g_tuning.staged = staged_mode; }
 void conv_set_split(int mode) { g_tuning.split = mode; }
 void conv_set_resident(int mode) { g_tuning.resident = mode; }
+void conv_set_pool_smem(int mode) { g_tuning.pool_smem = mode; }
 void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps) {
   g_tuning.pair_mode = pair_mode;
   g_tuning.a_stages = a_stages;
@@ -971,7 +1047,8 @@ static int launch2(const CUtensorMap& tx, const CUtensorMap& tw, const Conv2Para
   auto kern = conv_igemm2_tf32_kernel<BLOCK_N, MH, TPS, PAIR, STYLE, SPLIT>;
   const int smem = conv2_smem_bytes(p.a_stage_bytes, p.a_stages, p.b_stages, p.tps,
                                     Conv2Cfg<BLOCK_N, MH, PAIR>::kBRows, p.N, BLOCK_N, MH,
-                                    p.staged || p.mask_src != nullptr || p.add_src != nullptr,
+                                    p.staged || p.pool_smem || p.mask_src != nullptr ||
+                                        p.add_src != nullptr,
                                     p.w_resident ? p.w_res_bytes : 0);
   STV_REQUIRE(smem <= 227 * 1024, "conv_igemm2: %d bytes of shared memory exceed the SM", smem);
   const int dev = current_device();
@@ -1247,7 +1324,10 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
   const bool staged_pays = a.unpool_code != nullptr || (a.out_pre != nullptr && a.out_post != nullptr) ||
                            (a.out_pre != nullptr && a.out_post == nullptr && a.out_pool == nullptr);
   const bool want_staged = g_tuning.staged < 0 ? staged_pays : g_tuning.staged == 1;
-  if (!staging_needed && want_staged && N != 16 && tc.block_n <= 128) {
+  // the fused pool wants the tiles too (window maxima / routing bits without shuffles)
+  const bool want_pool_tiles = p.out_pool != nullptr && g_tuning.pool_smem != 0;
+  p.pool_smem = 0;
+  if (!staging_needed && (want_staged || want_pool_tiles) && N != 16 && tc.block_n <= 128) {
     auto depth_for = [&](bool stg) {
       int depth = p.uni ? (two_per_sm ? 2 : 4) : 4;
       if (p.uni && env_as > 0) depth = env_as;
@@ -1262,7 +1342,8 @@ int conv_igemm2_launch(const ConvArgs& a, cudaStream_t stream) {
         conv2_smem_bytes(p.a_stage_bytes, depth_for(true), depth_for(true), p.tps, b_rows, N,
                          tc.block_n, tc.mh, true, res_bytes) <= 227 * 1024) {
       staging = true;
-      p.staged = 1;
+      p.staged = want_staged ? 1 : 0;
+      p.pool_smem = want_pool_tiles ? 1 : 0;
     }
   }
   if (p.uni) {

@@ -51,6 +51,7 @@ void conv_set_tuning(int pair_mode, int a_stages, int b_stages, int tps);
 void conv_set_epilogue(int staged_mode);
 void conv_set_split(int mode);
 void conv_set_resident(int mode);
+void conv_set_pool_smem(int mode);
 int conv_plan_override(int H, int W, int C, int N, int backward, int block_n, int mh, int pair,
                        int depth, int tps);
 

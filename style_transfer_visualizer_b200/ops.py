@@ -458,6 +458,11 @@ def conv_set_resident(mode: int = -1) -> None:
     nat.call("stv_conv_set_resident", int(mode))
 
 
+def conv_set_pool_smem(mode: int = -1) -> None:
+    """-1: built-in rule, 0: fused pool by warp shuffles only (A/B runs)."""
+    nat.call("stv_conv_set_pool_smem", int(mode))
+
+
 def conv_plan_override(h: int = 0, w: int = 0, c: int = 0, n: int = 0, *, backward: bool = False,  # noqa: PLR0913
                        block_n: int = 0, m_halves: int = 0, pair: int = -1, depth: int = 0,
                        tps: int = 0) -> None:

@@ -66,6 +66,7 @@ def main() -> None:
     ap.add_argument("--layers", default="", help="comma list of layer indices to sweep (default all)")
     ap.add_argument("--ab-split", action="store_true",
                     help="only compare the split-K second issuer: off / rule / everywhere legal")
+    ap.add_argument("--ab-pool", action="store_true", help="only compare the two fused-pool epilogues")
     ap.add_argument("--ab-resident", action="store_true",
                     help="only compare weight-stationary 64->64 layers: off / rule")
     args = ap.parse_args()
@@ -80,6 +81,14 @@ def main() -> None:
                 us = time_step(model, x, opt, args.reps)
                 print(f"round {rnd} {name:32s}: {us:8.1f} us/step ({1e6 / us:6.1f} steps/s)", flush=True)
         ops.conv_set_resident()
+        return
+    if args.ab_pool:
+        for rnd in range(2):
+            for mode, name in ((0, "pool by shuffles"), (-1, "rule (pool through the staging tile)")):
+                ops.conv_set_pool_smem(mode)
+                us = time_step(model, x, opt, args.reps)
+                print(f"round {rnd} {name:36s}: {us:8.1f} us/step ({1e6 / us:6.1f} steps/s)", flush=True)
+        ops.conv_set_pool_smem()
         return
     if args.ab_split:
         for rnd in range(2):
