@@ -312,7 +312,19 @@ class OptimizationRunner:
             self._latest_logged = logged
             metrics = StepMetrics(step=logged.step, style_loss=logged.style_loss,
                                   content_loss=logged.content_loss, total_loss=logged.total_loss)
-            self._flush_finite_checks()  # the host has just synced anyway
+            if self._graph_records and self._finite_steps == [logged.step]:
+                # the only pending step is the one whose three losses were just read back: its
+                # flags follow from those host values -- no second device-to-host copy (with
+                # log_every=1 that copy was a second sync in every step)
+                import math
+
+                self._finite_steps.clear()
+                for which, val in enumerate((logged.style_loss, logged.content_loss,
+                                             logged.total_loss)):
+                    if not math.isfinite(val):
+                        self._warn_non_finite(which, logged.step)
+            else:
+                self._flush_finite_checks()  # the host has just synced anyway
 
         self._maybe_write_video_frame(metrics)
         self.progress_bar.update(1)
