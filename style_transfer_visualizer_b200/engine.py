@@ -80,6 +80,7 @@ class _Workspace:
     scratch: torch.Tensor | None = None
     grad_img: torch.Tensor | None = None
     generation: int = 0
+    warm: bool = False   # a full forward + backward has run at this size (see Engine.is_warm)
     nbytes: int = 0
 
 
@@ -253,6 +254,13 @@ class VggLossEngine:
         st = self.stages[s]
         return (self.compact_backward and s > 0 and st.pool_idx is not None
                 and not self._stage_taps(st) and s + 1 < len(self.stages))
+
+    def is_warm(self, height: int, width: int) -> bool:
+        """True once a full forward + backward has run at this image size: workspaces are allocated
+        and the kernels' one-time attribute calls are done, so a step can be captured into a CUDA
+        graph without a dry run."""
+        ws = self._workspaces.get((height, width))
+        return bool(ws is not None and getattr(ws, "warm", False))
 
     def grad_buffer(self, height: int, width: int) -> torch.Tensor:
         """The NCHW buffer ``backward_losses`` writes for this image size."""
@@ -530,6 +538,7 @@ class VggLossEngine:
             else:
                 self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
         ops.conv3x3_first_dgrad_rows(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_img)
+        ws.warm = True  # every buffer of this size exists and every kernel variant has been launched
         return ws.grad_img
 
     # ------------------------------------------------------------------ introspection

@@ -107,12 +107,15 @@ class FusedStep:
 
     def _capture(self) -> None:
         with torch.no_grad():
-            # dry run without the update: allocates workspaces, sets kernel attributes
-            side = torch.cuda.Stream(device=self.x.device)
-            side.wait_stream(torch.cuda.current_stream(self.x.device))
-            with torch.cuda.stream(side):
-                self._forward_backward()
-            torch.cuda.current_stream(self.x.device).wait_stream(side)
+            # dry run without the update: allocates workspaces, sets kernel attributes -- only the
+            # first time this engine sees the image size (a second run on the same model, e.g. the
+            # next job of the same shape, captures straight away)
+            if not self.engine.is_warm(self.height, self.width):
+                side = torch.cuda.Stream(device=self.x.device)
+                side.wait_stream(torch.cuda.current_stream(self.x.device))
+                with torch.cuda.stream(side):
+                    self._forward_backward()
+                torch.cuda.current_stream(self.x.device).wait_stream(side)
             torch.cuda.synchronize(self.x.device)
             graph = torch.cuda.CUDAGraph()
             before = nat.launch_count()
