@@ -32,7 +32,8 @@ constexpr int kFirstCout = 64;
 //     values are loaded first: 272 us (4.06 TB/s).  What is left is the LSU data pipe (64 % busy: a
 //     128-bit shared load costs four wavefronts however many lanes share an address);
 //   16 pixels x one channel quad per thread (a quarter of the weight LDS, full-line stores, sign
-//     bits by redux.sync): 455 us -- rejected.
+//     bits by redux.sync): 455 us; 8 pixels x 8 channels (half the weight LDS, 236 registers, two
+//     CTAs per SM): 388 us -- both rejected: occupancy matters more here than LDS wavefronts.
 constexpr int kFirstPx = 4;
 constexpr int kFirstThreads = 128;
 constexpr int kFirstGroupsPerCta = kFirstThreads / 4;
