@@ -80,7 +80,7 @@ class _Workspace:
     scratch: torch.Tensor | None = None
     grad_img: torch.Tensor | None = None
     generation: int = 0
-    warm: bool = False   # a full forward + backward has run at this size (see Engine.is_warm)
+    warm: tuple | None = None   # option signature of the last full forward + backward at this size (Engine.is_warm)
     nbytes: int = 0
 
 
@@ -260,7 +260,10 @@ class VggLossEngine:
         and the kernels' one-time attribute calls are done, so a step can be captured into a CUDA
         graph without a dry run."""
         ws = self._workspaces.get((height, width))
-        return bool(ws is not None and getattr(ws, "warm", False))
+        return ws is not None and ws.warm == self._options_signature()
+
+    def _options_signature(self) -> tuple:
+        return (self.compact_backward, self.fuse_style_bwd, self.first_layer_tc, self.overlap_losses)
 
     def grad_buffer(self, height: int, width: int) -> torch.Tensor:
         """The NCHW buffer ``backward_losses`` writes for this image size."""
@@ -538,7 +541,8 @@ class VggLossEngine:
             else:
                 self._tap_grads(ws, st.conv_idx, ws.pre[s], d_y, grad_w, False)
         ops.conv3x3_first_dgrad_rows(ws.d_y[0], self.stages[0].w_dgrad, ws.grad_img)
-        ws.warm = True  # every buffer of this size exists and every kernel variant has been launched
+        # every buffer of this size exists and every kernel variant these options select has been launched
+        ws.warm = self._options_signature()
         return ws.grad_img
 
     # ------------------------------------------------------------------ introspection
