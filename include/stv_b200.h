@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STV_ABI_VERSION 3
+#define STV_ABI_VERSION 4
 
 const char* stv_last_error(void);
 int stv_abi_version(void);

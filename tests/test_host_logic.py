@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol() -> None:
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in stv_b200.h but not exported"
     assert declared == set(nat.EXPORTED_SYMBOLS)
-    assert lib.stv_abi_version() == 3
+    assert lib.stv_abi_version() == 4
     assert lib.stv_reduce_scratch_floats() > 0
     assert lib.stv_gram_workspace_bytes(64 * 64, 64) > 0
 
